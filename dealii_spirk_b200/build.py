@@ -1,0 +1,74 @@
+"""Build recipes (in-tree, no JIT cache): the CUDA device library, the C++ host library, and
+(test infrastructure) the CPU oracle libraries.  nvcc cross-compiles sm_100a without a GPU."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+DEVICE_LIB = os.path.join(HERE, "libspirk_b200.so")
+HOST_LIB = os.path.join(HERE, "libspirk_host.so")
+NVCC = os.environ.get("SPIRK_NVCC", "/usr/local/cuda/bin/nvcc")
+# the image exports CXX=/opt/gcc/bin/g++ (no libgomp.spec); use the distro compiler explicitly
+GXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+
+
+def device_sources():
+    d = os.path.join(HERE, "csrc")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [os.path.join(ROOT, "include", "spirk_b200.h")]
+
+
+def build_device(force=False, verbose_ptxas=False):
+    srcs = device_sources()
+    if not force and not _newer(DEVICE_LIB, srcs):
+        return DEVICE_LIB
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+           "-ccbin", GXX, "-Xcompiler", "-fPIC,-O3", "-o", DEVICE_LIB, os.path.join(HERE, "csrc", "spirk_b200.cu"),
+           "-ldl"]
+    if verbose_ptxas:
+        cmd.insert(1, "-Xptxas=-v")
+    _run(cmd)
+    return DEVICE_LIB
+
+
+def host_sources():
+    d = os.path.join(HERE, "host")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cc", ".h"))] + \
+        [os.path.join(ROOT, "include", "spirk_b200.h"), os.path.join(ROOT, "include", "spirk_host.h")]
+
+
+def build_host(force=False):
+    srcs = [s for s in host_sources() if os.path.exists(s)]
+    if not force and not _newer(HOST_LIB, srcs + [DEVICE_LIB]):
+        return HOST_LIB
+    ccs = [s for s in srcs if s.endswith(".cc")]
+    _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", HOST_LIB]
+         + ccs + ["-L" + HERE, "-lspirk_b200", "-Wl,-rpath,$ORIGIN"])
+    return HOST_LIB
+
+
+def build_oracle():
+    _run(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
+
+
+def build_all(force=False):
+    build_device(force)
+    build_host(force)
+    build_oracle()
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)

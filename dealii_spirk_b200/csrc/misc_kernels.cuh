@@ -1,0 +1,433 @@
+// Multigrid transfer, vector kernels, reductions, stage mixing and problem-setup kernels.
+#pragma once
+#include "op_v1.cuh"
+
+namespace spirk
+{
+  // =========================================================================================
+  // two-level transfer (deal.II MGTwoLevelTransfer set up in preconditioner.h:266-282)
+  // One thread block per (coarse cell, vector block); sum-factorised with the (2k+1) x (k+1)
+  // 1-D embedding P.  Prolongation writes every fine DoF exactly once (its owner coarse cell),
+  // restriction is the exact transpose (atomics into a zeroed coarse vector).
+  // =========================================================================================
+  template <int K, int DIM>
+  __global__ void __launch_bounds__(128)
+    k_prolongate_add(const Geo gf, const int nb, double *__restrict__ fine, const long long fs,
+                     const double *__restrict__ coarse, const long long cs)
+  {
+    constexpr int n = K + 1, m = 2 * K + 1;
+    constexpr int NC = (DIM == 3) ? n * n * n : n * n;          // coarse local
+    constexpr int N1 = (DIM == 3) ? n * n * m : n * m;          // x expanded
+    constexpr int N2 = (DIM == 3) ? n * m * m : m * m;          // x,y expanded
+    constexpr int N3 = (DIM == 3) ? m * m * m : 1;              // all expanded (3-D only)
+    __shared__ double sc[NC], s1[N1], s2[N2];
+    const double *P   = c_fe[K].P;
+    const int     ncc = gf.nc / 2, n1c = K * ncc + 1, n1f = gf.n1;
+    const long long ncells = (DIM == 3) ? (long long)ncc * ncc * ncc : (long long)ncc * ncc;
+    for (long long wi = blockIdx.x; wi < ncells * nb; wi += gridDim.x)
+      {
+        const int       b = wi / ncells;
+        const long long c = wi - b * ncells;
+        const int       cx = c % ncc, cy = (c / ncc) % ncc, cz = (DIM == 3) ? c / ((long long)ncc * ncc) : 0;
+        for (int l = threadIdx.x; l < NC; l += blockDim.x)
+          {
+            const int  ix = cx * K + l % n, iy = cy * K + (l / n) % n, iz = (DIM == 3) ? cz * K + l / (n * n) : 1;
+            const bool bd = on_bdry(ix, n1c) || on_bdry(iy, n1c) || (DIM == 3 && on_bdry(iz, n1c));
+            sc[l] = bd ? 0.0 : coarse[b * cs + ix + (long long)n1c * (iy + (DIM == 3 ? (long long)n1c * iz : 0))];
+          }
+        __syncthreads();
+        // expand x: s1[(zy)*m + fx] = sum_i P[fx][i] sc[(zy)*n + i]
+        for (int e = threadIdx.x; e < N1; e += blockDim.x)
+          {
+            const int fx = e % m, zy = e / m;
+            double    s  = 0.0;
+#pragma unroll
+            for (int i = 0; i < n; ++i)
+              s = fma(P[fx * n + i], sc[zy * n + i], s);
+            s1[e] = s;
+          }
+        __syncthreads();
+        // expand y: s2[(z*m + fy)*m + fx] = sum_j P[fy][j] s1[(z*n + j)*m + fx]
+        for (int e = threadIdx.x; e < N2; e += blockDim.x)
+          {
+            const int fx = e % m, fy = (e / m) % m, z = e / (m * m);
+            double    s  = 0.0;
+#pragma unroll
+            for (int j = 0; j < n; ++j)
+              s = fma(P[fy * n + j], s1[(z * n + j) * m + fx], s);
+            s2[e] = s;
+          }
+        __syncthreads();
+        const int mx = (cx == ncc - 1) ? m : m - 1, my = (cy == ncc - 1) ? m : m - 1;
+        if (DIM == 3)
+          {
+            const int mz = (cz == ncc - 1) ? m : m - 1;
+            for (int e = threadIdx.x; e < N3; e += blockDim.x)
+              {
+                const int fx = e % m, fy = (e / m) % m, fz = e / (m * m);
+                if (fx < mx && fy < my && fz < mz)
+                  {
+                    double s = 0.0;
+#pragma unroll
+                    for (int l = 0; l < n; ++l)
+                      s = fma(P[fz * n + l], s2[(l * m + fy) * m + fx], s);
+                    const long long gi = (cx * 2 * K + fx) + (long long)n1f * ((cy * 2 * K + fy) + (long long)n1f * (cz * 2 * K + fz));
+                    fine[b * fs + gi] += s;
+                  }
+              }
+          }
+        else
+          {
+            for (int e = threadIdx.x; e < N2; e += blockDim.x)
+              {
+                const int fx = e % m, fy = e / m;
+                if (fx < mx && fy < my)
+                  fine[b * fs + (cx * 2 * K + fx) + (long long)n1f * (cy * 2 * K + fy)] += s2[e];
+              }
+          }
+        __syncthreads();
+      }
+  }
+
+  template <int K, int DIM>
+  __global__ void __launch_bounds__(128)
+    k_restrict(const Geo gf, const int nb, double *__restrict__ coarse, const long long cs,
+               const double *__restrict__ fine, const long long fs)
+  {
+    constexpr int n = K + 1, m = 2 * K + 1;
+    constexpr int NF = (DIM == 3) ? m * m * m : m * m;          // fine local
+    constexpr int N2 = (DIM == 3) ? m * m * n : m * n;          // x contracted
+    constexpr int N1 = (DIM == 3) ? m * n * n : n * n;          // x,y contracted
+    constexpr int NC = (DIM == 3) ? n * n * n : n * n;
+    __shared__ double sf[NF], s2[N2], s1[N1];
+    const double *P   = c_fe[K].P;
+    const int     ncc = gf.nc / 2, n1c = K * ncc + 1, n1f = gf.n1;
+    const long long ncells = (DIM == 3) ? (long long)ncc * ncc * ncc : (long long)ncc * ncc;
+    for (long long wi = blockIdx.x; wi < ncells * nb; wi += gridDim.x)
+      {
+        const int       b = wi / ncells;
+        const long long c = wi - b * ncells;
+        const int       cx = c % ncc, cy = (c / ncc) % ncc, cz = (DIM == 3) ? c / ((long long)ncc * ncc) : 0;
+        const int       mx = (cx == ncc - 1) ? m : m - 1, my = (cy == ncc - 1) ? m : m - 1,
+                  mz = (DIM == 3) ? ((cz == ncc - 1) ? m : m - 1) : 1;
+        for (int e = threadIdx.x; e < NF; e += blockDim.x)
+          {
+            const int fx = e % m, fy = (e / m) % m, fz = (DIM == 3) ? e / (m * m) : 0;
+            double    v  = 0.0;
+            if (fx < mx && fy < my && fz < mz)
+              v = fine[b * fs + (cx * 2 * K + fx) + (long long)n1f * ((cy * 2 * K + fy) + (DIM == 3 ? (long long)n1f * (cz * 2 * K + fz) : 0))];
+            sf[e] = v;
+          }
+        __syncthreads();
+        // contract x: s2[(zy)*n + i] = sum_fx P[fx][i] sf[(zy)*m + fx]
+        for (int e = threadIdx.x; e < N2; e += blockDim.x)
+          {
+            const int i = e % n, zy = e / n;
+            double    s = 0.0;
+#pragma unroll
+            for (int fx = 0; fx < m; ++fx)
+              s = fma(P[fx * n + i], sf[zy * m + fx], s);
+            s2[e] = s;
+          }
+        __syncthreads();
+        // contract y: s1[(z*n + j)*n + i] = sum_fy P[fy][j] s2[(z*m + fy)*n + i]
+        for (int e = threadIdx.x; e < N1; e += blockDim.x)
+          {
+            const int i = e % n, j = (e / n) % n, z = e / (n * n);
+            double    s = 0.0;
+#pragma unroll
+            for (int fy = 0; fy < m; ++fy)
+              s = fma(P[fy * n + j], s2[(z * m + fy) * n + i], s);
+            s1[e] = s;
+          }
+        __syncthreads();
+        for (int e = threadIdx.x; e < NC; e += blockDim.x)
+          {
+            const int i = e % n, j = (e / n) % n, l = (DIM == 3) ? e / (n * n) : 0;
+            double    s;
+            if (DIM == 3)
+              {
+                s = 0.0;
+#pragma unroll
+                for (int fz = 0; fz < m; ++fz)
+                  s = fma(P[fz * n + l], s1[(fz * n + j) * n + i], s);
+              }
+            else
+              s = s1[e];
+            const int  ix = cx * K + i, iy = cy * K + j, iz = (DIM == 3) ? cz * K + l : 1;
+            const bool bd = on_bdry(ix, n1c) || on_bdry(iy, n1c) || (DIM == 3 && on_bdry(iz, n1c));
+            if (!bd)
+              atomicAdd(coarse + b * cs + ix + (long long)n1c * (iy + (DIM == 3 ? (long long)n1c * iz : 0)), s);
+          }
+        __syncthreads();
+      }
+  }
+
+  // y_b = A x_b, tiny dense (coarse-grid solve): one block per vector block
+  __global__ void k_dense_matvec(const int n, double *__restrict__ y, const double *__restrict__ x, const long long stride,
+                                 const double *__restrict__ A)
+  {
+    extern __shared__ double sx[];
+    const int                b = blockIdx.x;
+    for (int j = threadIdx.x; j < n; j += blockDim.x)
+      sx[j] = x[b * stride + j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j)
+          s = fma(A[(size_t)i * n + j], sx[j], s);
+        y[b * stride + i] = s;
+      }
+  }
+
+  // =========================================================================================
+  // vector kernels
+  // =========================================================================================
+#define SPIRK_GRID_STRIDE(i, n) \
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+  __global__ void k_set(double *x, const long long n, const double v) { SPIRK_GRID_STRIDE(i, n) x[i] = v; }
+  __global__ void k_scale(double *x, const long long n, const double a) { SPIRK_GRID_STRIDE(i, n) x[i] *= a; }
+  __global__ void k_axpy(double *y, const double a, const double *__restrict__ x, const long long n)
+  {
+    SPIRK_GRID_STRIDE(i, n) y[i] = fma(a, x[i], y[i]);
+  }
+  __global__ void k_sadd(double *y, const double s, const double a, const double *__restrict__ x, const long long n)
+  {
+    SPIRK_GRID_STRIDE(i, n) y[i] = s * y[i] + a * x[i];
+  }
+  __global__ void k_add2(double *y, const double a, const double *__restrict__ x, const double b,
+                         const double *__restrict__ z, const long long n)
+  {
+    SPIRK_GRID_STRIDE(i, n) y[i] += a * x[i] + b * z[i];
+  }
+  __global__ void k_equ(double *y, const double a, const double *__restrict__ x, const long long n)
+  {
+    SPIRK_GRID_STRIDE(i, n) y[i] = a * x[i];
+  }
+  struct BlockFactors
+  {
+    double f[SPIRK_MAX_BLOCKS];
+  };
+  __global__ void k_scale_pointwise(const int nb, const long long n, double *y, const double *__restrict__ d,
+                                    const double *__restrict__ x, const long long stride, const BlockFactors f)
+  {
+    SPIRK_GRID_STRIDE(e, n * nb)
+    {
+      const int       b = e / n;
+      const long long j = b * stride + (e - b * n);
+      y[j]              = f.f[b] * (d[j] * x[j]);
+    }
+  }
+
+  // block-level sum of `v` over the block into partials[blockIdx.x + slot*gridDim.x]
+  template <int T>
+  __device__ __forceinline__ void block_reduce_store(double v, double *partials)
+  {
+    __shared__ double sw[T / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0)
+      sw[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32)
+      {
+        v = (threadIdx.x < T / 32) ? sw[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0)
+          *partials = v;
+      }
+    __syncthreads();
+  }
+
+  constexpr int RT = 256; // reduction block size
+  __global__ void __launch_bounds__(RT) k_dot(const double *__restrict__ x, const double *__restrict__ y, const long long n,
+                                              double *partials)
+  {
+    double s = 0.0;
+    SPIRK_GRID_STRIDE(i, n) s = fma(x[i], y[i], s);
+    block_reduce_store<RT>(s, partials + blockIdx.x);
+  }
+  __global__ void __launch_bounds__(RT) k_sum(const double *__restrict__ x, const long long n, double *partials)
+  {
+    double s = 0.0;
+    SPIRK_GRID_STRIDE(i, n) s += x[i];
+    block_reduce_store<RT>(s, partials + blockIdx.x);
+  }
+  // v += a V; partial of v . W     (W may alias v)
+  __global__ void __launch_bounds__(RT) k_add_and_dot(double *v, const double a, const double *__restrict__ V, const double *W,
+                                                      const long long n, double *partials)
+  {
+    double s = 0.0;
+    SPIRK_GRID_STRIDE(i, n)
+    {
+      const double t = fma(a, V[i], v[i]);
+      const double w = (W == v) ? t : W[i];
+      v[i]           = t;
+      s              = fma(t, w, s);
+    }
+    block_reduce_store<RT>(s, partials + blockIdx.x);
+  }
+  // result[slot] = sum of partials[0..nblocks)   (fixed order: deterministic)
+  __global__ void __launch_bounds__(RT) k_finish(const double *__restrict__ partials, const int nblocks, double *result)
+  {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += RT)
+      s += partials[i];
+    block_reduce_store<RT>(s, result);
+  }
+
+  // stage mixing (main.cc:1100-1104, 1164-1168, 877-891, 1511-1529)
+  struct MixMatrix
+  {
+    double T[SPIRK_MAX_BLOCKS * SPIRK_MAX_BLOCKS];
+  };
+  template <int QI>
+  __global__ void k_mix(const int qo, double *dst, const long long ds, const double *__restrict__ src, const long long ss,
+                        const long long n, const MixMatrix T, const int add)
+  {
+    SPIRK_GRID_STRIDE(e, n)
+    {
+      double in[QI];
+#pragma unroll
+      for (int j = 0; j < QI; ++j)
+        in[j] = src[j * ss + e];
+      for (int i = 0; i < qo; ++i)
+        {
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < QI; ++j)
+            t = fma(T.T[i * QI + j], in[j], t); // entries below the cut-off were zeroed on the host
+          if (add)
+            dst[i * ds + e] += t;
+          else
+            dst[i * ds + e] = t;
+        }
+    }
+  }
+
+  // =========================================================================================
+  // problem pieces
+  // =========================================================================================
+  // out[i] = boundary ? 0 : t1[ix] t1[iy] t1[iz] * scale   (separable load vector / nodal solution)
+  __global__ void k_outer_product(const Geo g, const double *__restrict__ t1, const double scale, const int zero_bdry,
+                                  double *__restrict__ out)
+  {
+    SPIRK_GRID_STRIDE(i, g.N)
+    {
+      const int  ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? i / ((long long)g.n1 * g.n1) : 1;
+      const bool bd = on_bdry(ix, g.n1) || on_bdry(iy, g.n1) || (g.dim == 3 && on_bdry(iz, g.n1));
+      double     v  = t1[ix] * t1[iy] * scale;
+      if (g.dim == 3)
+        v *= t1[iz];
+      out[i] = (zero_bdry && bd) ? 0.0 : v;
+    }
+  }
+
+  __global__ void k_set_zero_bdry(const Geo g, const int nb, double *u, const long long stride)
+  {
+    SPIRK_GRID_STRIDE(e, g.N * nb)
+    {
+      const int       b  = e / g.N;
+      const long long i  = e - b * g.N;
+      const int       ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? i / ((long long)g.n1 * g.n1) : 1;
+      if (on_bdry(ix, g.n1) || on_bdry(iy, g.n1) || (g.dim == 3 && on_bdry(iz, g.n1)))
+        u[b * stride + i] = 0.0;
+    }
+  }
+
+  // L2 / Linf error against the analytical solution with QGauss(k+2) (main.cc:3436-3469).
+  // One block per cell; result[0] += sum w d^2 (atomicAdd), result[1] = max |d| (ordered-bit atomicMax).
+  template <int K, int DIM>
+  __global__ void __launch_bounds__(128) k_error_norms(const Geo g, const double *__restrict__ u, const double ft, double *result)
+  {
+    constexpr int n = K + 1, ne = K + 2;
+    constexpr int NL = (DIM == 3) ? n * n * n : n * n;
+    constexpr int N1 = (DIM == 3) ? n * n * ne : n * ne;
+    constexpr int N2 = (DIM == 3) ? n * ne * ne : ne * ne;
+    constexpr int NQ = (DIM == 3) ? ne * ne * ne : ne * ne;
+    __shared__ double su[NL], s1[N1], s2[N2], red[128];
+    const double *Be = c_fe[K].Be, *xe = c_fe[K].xe, *we = c_fe[K].we;
+    const int     nc = g.nc, n1 = g.n1;
+    const long long ncells = (DIM == 3) ? (long long)nc * nc * nc : (long long)nc * nc;
+    double          lsum = 0.0, lmax = 0.0;
+    const double    twopi = 6.283185307179586476925286766559;
+    for (long long c = blockIdx.x; c < ncells; c += gridDim.x)
+      {
+        const int cx = c % nc, cy = (c / nc) % nc, cz = (DIM == 3) ? c / ((long long)nc * nc) : 0;
+        for (int l = threadIdx.x; l < NL; l += blockDim.x)
+          {
+            const int ix = cx * K + l % n, iy = cy * K + (l / n) % n, iz = (DIM == 3) ? cz * K + l / (n * n) : 0;
+            su[l]        = u[ix + (long long)n1 * (iy + (long long)n1 * iz)];
+          }
+        __syncthreads();
+        for (int e = threadIdx.x; e < N1; e += blockDim.x)
+          {
+            const int qx = e % ne, zy = e / ne;
+            double    s  = 0.0;
+            for (int i = 0; i < n; ++i)
+              s = fma(Be[qx * n + i], su[zy * n + i], s);
+            s1[e] = s;
+          }
+        __syncthreads();
+        for (int e = threadIdx.x; e < N2; e += blockDim.x)
+          {
+            const int qx = e % ne, qy = (e / ne) % ne, z = e / (ne * ne);
+            double    s  = 0.0;
+            for (int j = 0; j < n; ++j)
+              s = fma(Be[qy * n + j], s1[(z * n + j) * ne + qx], s);
+            s2[e] = s;
+          }
+        __syncthreads();
+        for (int e = threadIdx.x; e < NQ; e += blockDim.x)
+          {
+            const int qx = e % ne, qy = (e / ne) % ne, qz = (DIM == 3) ? e / (ne * ne) : 0;
+            double    v;
+            if (DIM == 3)
+              {
+                v = 0.0;
+                for (int l = 0; l < n; ++l)
+                  v = fma(Be[qz * n + l], s2[(l * ne + qy) * ne + qx], v);
+              }
+            else
+              v = s2[e];
+            double ex = sin(twopi * (cx + xe[qx]) * g.h) * sin(twopi * (cy + xe[qy]) * g.h) * ft;
+            double w  = we[qx] * we[qy] * g.h * g.h;
+            if (DIM == 3)
+              {
+                ex *= sin(twopi * (cz + xe[qz]) * g.h);
+                w *= we[qz] * g.h;
+              }
+            const double d = v - ex;
+            lsum           = fma(w * d, d, lsum);
+            lmax           = fmax(lmax, fabs(d));
+          }
+        __syncthreads();
+      }
+    red[threadIdx.x] = lsum;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1)
+      {
+        if (threadIdx.x < o)
+          red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+      }
+    if (threadIdx.x == 0)
+      atomicAdd(result, red[0]);
+    __syncthreads();
+    red[threadIdx.x] = lmax;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1)
+      {
+        if (threadIdx.x < o)
+          red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+      }
+    if (threadIdx.x == 0)
+      atomicMax((unsigned long long *)(result + 1), (unsigned long long)__double_as_longlong(red[0]));
+  }
+} // namespace spirk

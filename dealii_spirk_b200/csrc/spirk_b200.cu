@@ -1,0 +1,811 @@
+// Implementation of include/spirk_b200.h with hand-written CUDA kernels for sm_100a.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC ...
+// There is NO CPU fallback in this library: every entry point needs a CUDA device.
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "fe1d.h"
+#include "misc_kernels.cuh"
+#include "nccl_dl.h"
+#include "op_v2.cuh"
+
+namespace spirk
+{
+  thread_local std::string g_last_error;
+  int                      set_error(int code, const std::string &msg)
+  {
+    g_last_error = msg;
+    return code;
+  }
+
+  static Fe1D       g_fe[SPIRK_MAX_DEGREE + 1];
+  static std::mutex g_fe_mutex;
+  static bool       g_fe_host_ready = false;
+
+  static void init_fe_host()
+  {
+    std::lock_guard<std::mutex> lock(g_fe_mutex);
+    if (!g_fe_host_ready)
+      {
+        for (int k = 1; k <= SPIRK_MAX_DEGREE; ++k)
+          g_fe[k] = make_fe1d(k);
+        g_fe_host_ready = true;
+      }
+  }
+
+  int upload_fe_constants()
+  {
+    init_fe_host();
+    static FeConst all[SPIRK_MAX_DEGREE + 1];
+    std::memset(all, 0, sizeof(all));
+    for (int k = 1; k <= SPIRK_MAX_DEGREE; ++k)
+      {
+        const Fe1D &f = g_fe[k];
+        const int   n = f.n;
+        for (int i = 0; i < n * n; ++i)
+          all[k].Mh[i] = f.Mh[i], all[k].Kh[i] = f.Kh[i];
+        for (int i = 0; i < (2 * k + 1) * n; ++i)
+          all[k].P[i] = f.P[i];
+        for (int i = 0; i < (k + 2) * n; ++i)
+          all[k].Be[i] = f.Be[i];
+        for (int i = 0; i < k + 2; ++i)
+          all[k].xe[i] = f.xe[i], all[k].we[i] = f.we[i];
+        for (int i = 0; i < n; ++i)
+          all[k].nodes[i] = f.nodes[i];
+      }
+    SPIRK_CUDA(cudaMemcpyToSymbol(c_fe, all, sizeof(all)));
+    return SPIRK_OK;
+  }
+
+  int ensure_scratch(spirk_ctx *ctx, size_t n)
+  {
+    if (ctx->scratch_cap < n)
+      {
+        if (ctx->d_scratch)
+          {
+            SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+            SPIRK_CUDA(cudaFree(ctx->d_scratch));
+          }
+        ctx->d_scratch = nullptr, ctx->scratch_cap = 0;
+        SPIRK_CUDA(cudaMalloc(&ctx->d_scratch, n * sizeof(double)));
+        ctx->scratch_cap = n;
+      }
+    return SPIRK_OK;
+  }
+
+  int ensure_tab(spirk_ctx *ctx, size_t n)
+  {
+    if (ctx->tab_cap < n)
+      {
+        if (ctx->d_tab)
+          {
+            SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+            SPIRK_CUDA(cudaFree(ctx->d_tab));
+          }
+        ctx->d_tab = nullptr, ctx->tab_cap = 0;
+        SPIRK_CUDA(cudaMalloc(&ctx->d_tab, n * sizeof(double)));
+        ctx->tab_cap = n;
+      }
+    return SPIRK_OK;
+  }
+
+  static int check_level(const spirk_level *l)
+  {
+    if (!l || (l->dim != 2 && l->dim != 3) || l->n_cells_1d < 1)
+      return set_error(SPIRK_ERR_INVALID, "bad level descriptor");
+    if (l->degree < 1 || l->degree > SPIRK_MAX_DEGREE)
+      return set_error(SPIRK_ERR_UNSUPPORTED, "degree must be 1..6");
+    return SPIRK_OK;
+  }
+
+  static int check_op(const spirk_opdesc *op)
+  {
+    if (!op || op->nb < 1 || op->nb > SPIRK_MAX_BLOCKS || (op->kind != SPIRK_OP_REAL && op->kind != SPIRK_OP_COUPLED))
+      return set_error(SPIRK_ERR_INVALID, "bad operator descriptor");
+    return SPIRK_OK;
+  }
+
+  OpDev make_opdev(const Geo &g, const spirk_opdesc *op)
+  {
+    OpDev        d;
+    const double hd = std::pow(g.h, g.dim), hl = std::pow(g.h, g.dim - 2);
+    d.nb = op->nb;
+    for (int b = 0; b < op->nb; ++b)
+      {
+        d.cm[b] = op->mass[b] * hd;
+        d.cl[b] = op->laplace[b] * hl;
+        for (int j = 0; j < op->nb; ++j)
+          d.cc[b * op->nb + j] = (op->kind == SPIRK_OP_COUPLED) ? op->coupling[b * op->nb + j] * hd : 0.0;
+      }
+    return d;
+  }
+
+  static inline int grid_for(const spirk_ctx *ctx, long long n, int threads, int per_sm = 8)
+  {
+    long long blocks = (n + threads - 1) / threads;
+    long long cap    = (long long)ctx->n_sms * per_sm;
+    return (int)std::max<long long>(1, std::min(blocks, cap));
+  }
+
+  template <int K>
+  static int launch_apply_v1(spirk_ctx *ctx, const Geo &g, const OpDev &od, bool coupled, double *dst, const double *src,
+                             long long stride)
+  {
+    using C = CfgV1<K>;
+    k_init_dst<<<grid_for(ctx, g.N * od.nb, 256), 256, 0, ctx->stream>>>(g, od.nb, dst, src, stride);
+    SPIRK_LAUNCH_CHECK(ctx);
+    if (g.dim == 3)
+      {
+        const long long ncells = (long long)g.nc * g.nc * g.nc, nbatch = (ncells + C::CPB3 - 1) / C::CPB3;
+        const int       grid   = (int)std::min<long long>(nbatch, (long long)ctx->n_sms * 8);
+        if (coupled)
+          k_apply3d_v1<K, true><<<grid, C::T3, 0, ctx->stream>>>(g, od, dst, src, stride);
+        else
+          k_apply3d_v1<K, false><<<grid, C::T3, 0, ctx->stream>>>(g, od, dst, src, stride);
+      }
+    else
+      {
+        const long long ncells = (long long)g.nc * g.nc, nbatch = (ncells + C::CPB2 - 1) / C::CPB2;
+        const int       grid   = (int)std::min<long long>(nbatch, (long long)ctx->n_sms * 8);
+        if (coupled)
+          k_apply2d_v1<K, true><<<grid, C::T2, 0, ctx->stream>>>(g, od, dst, src, stride);
+        else
+          k_apply2d_v1<K, false><<<grid, C::T2, 0, ctx->stream>>>(g, od, dst, src, stride);
+      }
+    SPIRK_LAUNCH_CHECK(ctx);
+    return SPIRK_OK;
+  }
+
+#define SPIRK_DISPATCH_K(k, expr)                                           \
+  switch (k)                                                                \
+    {                                                                       \
+      case 1: { constexpr int K = 1; expr; } break;                         \
+      case 2: { constexpr int K = 2; expr; } break;                         \
+      case 3: { constexpr int K = 3; expr; } break;                         \
+      case 4: { constexpr int K = 4; expr; } break;                         \
+      case 5: { constexpr int K = 5; expr; } break;                         \
+      case 6: { constexpr int K = 6; expr; } break;                         \
+      default: return set_error(SPIRK_ERR_UNSUPPORTED, "degree");          \
+    }
+
+  // dst = A src with the variant selected by the context; mode-specific fused paths in op_v2
+  static int apply_any(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, double *dst, const double *src, long long stride)
+  {
+    const OpDev od      = make_opdev(g, op);
+    const bool  coupled = op->kind == SPIRK_OP_COUPLED;
+    int         st      = SPIRK_OK;
+    SPIRK_DISPATCH_K(g.k, st = launch_apply_v1<K>(ctx, g, od, coupled, dst, src, stride));
+    return st;
+  }
+
+  int finish_reduction(spirk_ctx *ctx, int n_results, int n_blocks, double *host_out)
+  {
+    for (int r = 0; r < n_results; ++r)
+      {
+        k_finish<<<1, RT, 0, ctx->stream>>>(ctx->d_partials + (size_t)r * n_blocks, n_blocks, ctx->d_result + r);
+        SPIRK_LAUNCH_CHECK(ctx);
+      }
+    if (ctx->reduction_comm)
+      if (int e = spirk_comm_allreduce_sum(ctx, ctx->reduction_comm, ctx->d_result, n_results))
+        return e;
+    SPIRK_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, n_results * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < n_results; ++r)
+      host_out[r] = ctx->h_result[r];
+    return SPIRK_OK;
+  }
+} // namespace spirk
+
+using namespace spirk;
+
+struct spirk_comm
+{
+  ncclComm_t comm = nullptr;
+  int        rank = 0, n_ranks = 1;
+};
+
+#define SPIRK_NCCL(call)                                                                                     \
+  do                                                                                                         \
+    {                                                                                                        \
+      const NcclApi &nccl = nccl_api();                                                                      \
+      if (!nccl.ok)                                                                                          \
+        return set_error(SPIRK_ERR_COMM, nccl.error);                                                        \
+      ncclResult_t r__ = (call);                                                                             \
+      if (r__ != ncclSuccess)                                                                                \
+        return set_error(SPIRK_ERR_COMM, std::string(#call) + ": " + nccl.GetErrorString(r__));             \
+    }                                                                                                        \
+  while (0)
+
+extern "C" {
+
+const char *spirk_backend(void) { return "cuda-sm_100a"; }
+const char *spirk_last_error(void) { return g_last_error.c_str(); }
+
+int spirk_ctx_create(spirk_ctx **out, int device)
+{
+  if (!out)
+    return set_error(SPIRK_ERR_INVALID, "null ctx pointer");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return set_error(SPIRK_ERR_DEVICE, "no CUDA device available — this library has no CPU fallback");
+  if (device < 0 || device >= count)
+    return set_error(SPIRK_ERR_INVALID, "device index out of range");
+  SPIRK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SPIRK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return set_error(SPIRK_ERR_DEVICE, "kernels are compiled for sm_100a only");
+  spirk_ctx *ctx = new spirk_ctx();
+  ctx->device    = device;
+  ctx->n_sms     = prop.multiProcessorCount;
+  SPIRK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  ctx->n_partials = ctx->n_sms * 8 * 4;
+  SPIRK_CUDA(cudaMalloc(&ctx->d_partials, ctx->n_partials * sizeof(double)));
+  SPIRK_CUDA(cudaMalloc(&ctx->d_result, 64 * sizeof(double)));
+  SPIRK_CUDA(cudaMallocHost(&ctx->h_result, 64 * sizeof(double)));
+  SPIRK_CUDA(cudaEventCreate(&ctx->ev0));
+  SPIRK_CUDA(cudaEventCreate(&ctx->ev1));
+  if (int e = upload_fe_constants())
+    return e;
+  *out = ctx;
+  return SPIRK_OK;
+}
+
+int spirk_ctx_destroy(spirk_ctx *ctx)
+{
+  if (!ctx)
+    return SPIRK_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_partials);
+  cudaFree(ctx->d_result);
+  cudaFreeHost(ctx->h_result);
+  cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_tab);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SPIRK_OK;
+}
+
+int spirk_ctx_sync(spirk_ctx *ctx)
+{
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPIRK_OK;
+}
+long long spirk_ctx_launch_count(spirk_ctx *ctx) { return ctx->launches; }
+int       spirk_ctx_timer_begin(spirk_ctx *ctx)
+{
+  SPIRK_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  return SPIRK_OK;
+}
+int spirk_ctx_timer_end(spirk_ctx *ctx, double *ms)
+{
+  SPIRK_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  SPIRK_CUDA(cudaEventSynchronize(ctx->ev1));
+  float f = 0;
+  SPIRK_CUDA(cudaEventElapsedTime(&f, ctx->ev0, ctx->ev1));
+  *ms = f;
+  return SPIRK_OK;
+}
+int spirk_ctx_set_option(spirk_ctx *ctx, const char *name, int value)
+{
+  if (std::strcmp(name, "apply_variant") == 0)
+    {
+      ctx->opt_apply_variant = value;
+      return SPIRK_OK;
+    }
+  return set_error(SPIRK_ERR_INVALID, std::string("unknown option ") + name);
+}
+
+int spirk_malloc(spirk_ctx *ctx, double **ptr, size_t n)
+{
+  (void)ctx;
+  if (cudaMalloc(ptr, (n ? n : 1) * sizeof(double)) != cudaSuccess)
+    {
+      cudaGetLastError();
+      return set_error(SPIRK_ERR_NOMEM, "cudaMalloc failed");
+    }
+  SPIRK_CUDA(cudaMemsetAsync(*ptr, 0, (n ? n : 1) * sizeof(double), ctx->stream));
+  return SPIRK_OK;
+}
+int spirk_free(spirk_ctx *ctx, double *ptr)
+{
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  SPIRK_CUDA(cudaFree(ptr));
+  return SPIRK_OK;
+}
+int spirk_copy_h2d(spirk_ctx *ctx, double *dst, const double *src, size_t n)
+{
+  SPIRK_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPIRK_OK;
+}
+int spirk_copy_d2h(spirk_ctx *ctx, double *dst, const double *src, size_t n)
+{
+  SPIRK_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return SPIRK_OK;
+}
+int spirk_malloc_host(spirk_ctx *, double **ptr, size_t n)
+{
+  SPIRK_CUDA(cudaMallocHost(ptr, (n ? n : 1) * sizeof(double)));
+  return SPIRK_OK;
+}
+int spirk_free_host(spirk_ctx *, double *ptr)
+{
+  SPIRK_CUDA(cudaFreeHost(ptr));
+  return SPIRK_OK;
+}
+
+long long spirk_level_n_dofs(const spirk_level *lvl) { return make_geo(lvl).N; }
+
+// ------------------------------------------------------------------------------- operator
+int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst, const double *src,
+                   long long stride)
+{
+  if (int e = check_level(lvl))
+    return e;
+  if (int e = check_op(op))
+    return e;
+  if (dst == src)
+    return set_error(SPIRK_ERR_INVALID, "op_apply: dst must not alias src");
+  const Geo g = make_geo(lvl);
+  if (ctx->opt_apply_variant != 1)
+    {
+      int st = v2_apply(ctx, g, op, V2_APPLY, dst, src, nullptr, nullptr, nullptr, stride, nullptr, nullptr);
+      if (st != SPIRK_ERR_UNSUPPORTED)
+        return st;
+    }
+  return apply_any(ctx, g, op, dst, src, stride);
+}
+
+int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst, const double *rhs,
+                      const double *src, long long stride)
+{
+  if (int e = check_level(lvl))
+    return e;
+  if (int e = check_op(op))
+    return e;
+  if (dst == src)
+    return set_error(SPIRK_ERR_INVALID, "op_residual: dst must not alias src");
+  const Geo g = make_geo(lvl);
+  if (ctx->opt_apply_variant != 1)
+    {
+      int st = v2_apply(ctx, g, op, V2_RESIDUAL, dst, src, nullptr, rhs, nullptr, stride, nullptr, nullptr);
+      if (st != SPIRK_ERR_UNSUPPORTED)
+        return st;
+    }
+  if (int e = ensure_scratch(ctx, (size_t)g.N * op->nb))
+    return e;
+  if (int e = apply_any(ctx, g, op, ctx->d_scratch, src, g.N))
+    return e;
+  k_residual_epilogue<<<grid_for(ctx, g.N * op->nb, 256), 256, 0, ctx->stream>>>(g.N, op->nb, dst, rhs, ctx->d_scratch, stride, g.N);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
+int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
+                       const double *f2)
+{
+  if (int e = check_level(lvl))
+    return e;
+  if (int e = check_op(op))
+    return e;
+  if (x_new == x)
+    return set_error(SPIRK_ERR_INVALID, "op_cheb_step: x_new must not alias x (it may alias x_old)");
+  const Geo g = make_geo(lvl);
+  if (ctx->opt_apply_variant != 1)
+    {
+      int st = v2_apply(ctx, g, op, V2_CHEB, x_new, x, x_old, rhs, dinv, stride, f1, f2);
+      if (st != SPIRK_ERR_UNSUPPORTED)
+        return st;
+    }
+  if (int e = ensure_scratch(ctx, (size_t)g.N * op->nb))
+    return e;
+  if (int e = apply_any(ctx, g, op, ctx->d_scratch, x, g.N))
+    return e;
+  ChebFactors f;
+  for (int b = 0; b < op->nb; ++b)
+    f.f1[b] = f1[b], f.f2[b] = f2[b];
+  k_cheb_epilogue<<<grid_for(ctx, g.N * op->nb, 256), 256, 0, ctx->stream>>>(g.N, op->nb, x_new, x, x_old, rhs, dinv, ctx->d_scratch,
+                                                                              stride, g.N, f);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
+int spirk_op_inverse_diagonal(spirk_ctx *ctx, const spirk_level *lvl, double *diag, double mass, double laplace)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo    g  = make_geo(lvl);
+  const double cm = mass * std::pow(g.h, g.dim), cl = laplace * std::pow(g.h, g.dim - 2);
+  SPIRK_DISPATCH_K(g.k, (k_inverse_diagonal<K><<<grid_for(ctx, g.N, 256), 256, 0, ctx->stream>>>(g, cm, cl, diag)));
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
+int spirk_op_assemble_dense(spirk_ctx *ctx, const spirk_level *lvl, double mass, double laplace, double *host_matrix)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo g = make_geo(lvl);
+  if (g.N > 4096)
+    return set_error(SPIRK_ERR_INVALID, "assemble_dense: level too large");
+  spirk_opdesc op;
+  std::memset(&op, 0, sizeof(op));
+  op.kind = SPIRK_OP_REAL, op.nb = 1, op.mass[0] = mass, op.laplace[0] = laplace;
+  const size_t N = g.N;
+  double      *d_e = nullptr, *d_c = nullptr;
+  SPIRK_CUDA(cudaMalloc(&d_e, N * sizeof(double)));
+  SPIRK_CUDA(cudaMalloc(&d_c, N * N * sizeof(double)));
+  std::vector<double> cols(N * N);
+  int                 st = SPIRK_OK;
+  for (size_t j = 0; j < N && st == SPIRK_OK; ++j)
+    {
+      cudaMemsetAsync(d_e, 0, N * sizeof(double), ctx->stream);
+      k_set<<<1, 1, 0, ctx->stream>>>(d_e + j, 1, 1.0);
+      ctx->launches++;
+      st = apply_any(ctx, g, &op, d_c + j * N, d_e, N);
+    }
+  if (st == SPIRK_OK)
+    {
+      cudaMemcpyAsync(cols.data(), d_c, N * N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      for (size_t i = 0; i < N; ++i)
+        for (size_t j = 0; j < N; ++j)
+          host_matrix[i * N + j] = cols[j * N + i];
+    }
+  cudaFree(d_e);
+  cudaFree(d_c);
+  return st;
+}
+
+// ------------------------------------------------------------------------------- transfer
+int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, double *fine, long long fs, const double *coarse,
+                            long long cs)
+{
+  if (int e = check_level(lf))
+    return e;
+  if (lf->n_cells_1d % 2)
+    return set_error(SPIRK_ERR_INVALID, "prolongate: fine level needs an even number of cells");
+  const Geo       g      = make_geo(lf);
+  const long long ncc    = g.nc / 2;
+  const long long ncells = (g.dim == 3 ? ncc * ncc * ncc : ncc * ncc) * nb;
+  const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 16);
+  if (g.dim == 3)
+    {
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_add<K, 3><<<grid, 128, 0, ctx->stream>>>(g, nb, fine, fs, coarse, cs)));
+    }
+  else
+    {
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_add<K, 2><<<grid, 128, 0, ctx->stream>>>(g, nb, fine, fs, coarse, cs)));
+    }
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
+int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coarse, long long cs, const double *fine,
+                      long long fs)
+{
+  if (int e = check_level(lf))
+    return e;
+  if (lf->n_cells_1d % 2)
+    return set_error(SPIRK_ERR_INVALID, "restrict: fine level needs an even number of cells");
+  const Geo   g  = make_geo(lf);
+  spirk_level lc = *lf;
+  lc.n_cells_1d /= 2;
+  const Geo gc = make_geo(&lc);
+  for (int b = 0; b < nb; ++b)
+    SPIRK_CUDA(cudaMemsetAsync(coarse + b * cs, 0, gc.N * sizeof(double), ctx->stream));
+  const long long ncc    = g.nc / 2;
+  const long long ncells = (g.dim == 3 ? ncc * ncc * ncc : ncc * ncc) * nb;
+  const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 16);
+  if (g.dim == 3)
+    {
+      SPIRK_DISPATCH_K(g.k, (k_restrict<K, 3><<<grid, 128, 0, ctx->stream>>>(g, nb, coarse, cs, fine, fs)));
+    }
+  else
+    {
+      SPIRK_DISPATCH_K(g.k, (k_restrict<K, 2><<<grid, 128, 0, ctx->stream>>>(g, nb, coarse, cs, fine, fs)));
+    }
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
+int spirk_dense_matvec(spirk_ctx *ctx, int n, int nb, double *y, const double *x, long long stride, const double *matrix)
+{
+  if (n < 1 || n > 4096 || y == x)
+    return set_error(SPIRK_ERR_INVALID, "dense_matvec: bad size or aliasing");
+  k_dense_matvec<<<nb, 128, n * sizeof(double), ctx->stream>>>(n, y, x, stride, matrix);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
+// ------------------------------------------------------------------------------- vectors
+#define VEC_LAUNCH(kernel, n, ...)                                                       \
+  do                                                                                     \
+    {                                                                                    \
+      if ((n) > 0)                                                                       \
+        {                                                                                \
+          kernel<<<grid_for(ctx, (n), 256), 256, 0, ctx->stream>>>(__VA_ARGS__);         \
+          SPIRK_LAUNCH_CHECK(ctx);                                                       \
+        }                                                                                \
+    }                                                                                    \
+  while (0)
+
+int spirk_vec_set(spirk_ctx *ctx, double *x, long long n, double v)
+{
+  VEC_LAUNCH(k_set, n, x, n, v);
+  return SPIRK_OK;
+}
+int spirk_vec_copy(spirk_ctx *ctx, double *dst, const double *src, long long n)
+{
+  SPIRK_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  return SPIRK_OK;
+}
+int spirk_vec_scale(spirk_ctx *ctx, double *x, long long n, double a)
+{
+  VEC_LAUNCH(k_scale, n, x, n, a);
+  return SPIRK_OK;
+}
+int spirk_vec_axpy(spirk_ctx *ctx, double *y, double a, const double *x, long long n)
+{
+  VEC_LAUNCH(k_axpy, n, y, a, x, n);
+  return SPIRK_OK;
+}
+int spirk_vec_sadd(spirk_ctx *ctx, double *y, double s, double a, const double *x, long long n)
+{
+  VEC_LAUNCH(k_sadd, n, y, s, a, x, n);
+  return SPIRK_OK;
+}
+int spirk_vec_add2(spirk_ctx *ctx, double *y, double a, const double *x, double b, const double *z, long long n)
+{
+  VEC_LAUNCH(k_add2, n, y, a, x, b, z, n);
+  return SPIRK_OK;
+}
+int spirk_vec_equ(spirk_ctx *ctx, double *y, double a, const double *x, long long n)
+{
+  VEC_LAUNCH(k_equ, n, y, a, x, n);
+  return SPIRK_OK;
+}
+int spirk_vec_scale_pointwise(spirk_ctx *ctx, int nb, long long n, double *y, const double *d, const double *x,
+                              long long stride, const double *f)
+{
+  if (nb < 1 || nb > SPIRK_MAX_BLOCKS)
+    return set_error(SPIRK_ERR_INVALID, "scale_pointwise: nb");
+  BlockFactors bf;
+  for (int b = 0; b < nb; ++b)
+    bf.f[b] = f[b];
+  VEC_LAUNCH(k_scale_pointwise, n * nb, nb, n, y, d, x, stride, bf);
+  return SPIRK_OK;
+}
+
+static inline int reduction_grid(const spirk_ctx *ctx, long long n)
+{
+  long long blocks = (n + RT * 4 - 1) / (RT * 4);
+  return (int)std::max<long long>(1, std::min<long long>(blocks, ctx->n_sms * 8));
+}
+
+int spirk_vec_dot(spirk_ctx *ctx, const double *x, const double *y, long long n, double *host_result)
+{
+  const int grid = reduction_grid(ctx, n);
+  k_dot<<<grid, RT, 0, ctx->stream>>>(x, y, n, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return finish_reduction(ctx, 1, grid, host_result);
+}
+int spirk_vec_add_and_dot(spirk_ctx *ctx, double *v, double a, const double *V, const double *W, long long n,
+                          double *host_result)
+{
+  const int grid = reduction_grid(ctx, n);
+  k_add_and_dot<<<grid, RT, 0, ctx->stream>>>(v, a, V, W, n, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return finish_reduction(ctx, 1, grid, host_result);
+}
+int spirk_vec_sum(spirk_ctx *ctx, const double *x, long long n, double *host_result)
+{
+  const int grid = reduction_grid(ctx, n);
+  k_sum<<<grid, RT, 0, ctx->stream>>>(x, n, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return finish_reduction(ctx, 1, grid, host_result);
+}
+
+int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *basis, long long bs, int dim, long long n, double *h,
+                    double *norm)
+{
+  if (dim < 1)
+    return set_error(SPIRK_ERR_INVALID, "gmres_mgs: dim");
+  if (int e = spirk_vec_dot(ctx, vv, basis, n, &h[0]))
+    return e;
+  for (int i = 1; i < dim; ++i)
+    if (int e = spirk_vec_add_and_dot(ctx, vv, -h[i - 1], basis + (i - 1) * bs, basis + i * bs, n, &h[i]))
+      return e;
+  double s = 0;
+  if (int e = spirk_vec_add_and_dot(ctx, vv, -h[dim - 1], basis + (dim - 1) * bs, vv, n, &s))
+    return e;
+  *norm = std::sqrt(s);
+  return SPIRK_OK;
+}
+
+int spirk_mix(spirk_ctx *ctx, int qo, int qi, double *dst, long long ds, const double *src, long long ss, long long n,
+              const double *T, int add, double cutoff)
+{
+  if (qo < 1 || qi < 1 || qo > SPIRK_MAX_BLOCKS || qi > SPIRK_MAX_BLOCKS)
+    return set_error(SPIRK_ERR_INVALID, "mix: block counts");
+  if (dst == src)
+    return set_error(SPIRK_ERR_INVALID, "mix: dst must not alias src");
+  MixMatrix M;
+  for (int i = 0; i < qo; ++i)
+    for (int j = 0; j < qi; ++j)
+      M.T[i * qi + j] = (std::fabs(T[i * qi + j]) > cutoff) ? T[i * qi + j] : 0.0;
+  const int grid = grid_for(ctx, n, 256);
+#define MIX_CASE(Q) \
+  case Q: k_mix<Q><<<grid, 256, 0, ctx->stream>>>(qo, dst, ds, src, ss, n, M, add); break;
+  switch (qi)
+    {
+      MIX_CASE(1) MIX_CASE(2) MIX_CASE(3) MIX_CASE(4) MIX_CASE(5) MIX_CASE(6) MIX_CASE(7) MIX_CASE(8)
+      MIX_CASE(9) MIX_CASE(10) MIX_CASE(11) MIX_CASE(12) MIX_CASE(13) MIX_CASE(14) MIX_CASE(15) MIX_CASE(16)
+    }
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
+// ------------------------------------------------------------------------------- problem
+static int upload_tab(spirk_ctx *ctx, const std::vector<double> &t)
+{
+  if (int e = ensure_tab(ctx, t.size()))
+    return e;
+  SPIRK_CUDA(cudaMemcpyAsync(ctx->d_tab, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream)); // t is a stack object of the caller
+  return SPIRK_OK;
+}
+
+int spirk_problem_rhs_spatial(spirk_ctx *ctx, const spirk_level *lvl, double *r)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo   g = make_geo(lvl);
+  const Fe1D &f = g_fe[g.k];
+  // separable forcing (main.cc:3523-3539): r = r1 (x) r1 [(x) r1],
+  // r1_i = sum_cells sum_q phi_i(x_q) sin(2 pi x_q) w_q h
+  std::vector<double> r1(g.n1, 0.0);
+  for (int c = 0; c < g.nc; ++c)
+    for (int q = 0; q < f.n; ++q)
+      {
+        const double s = std::sin(2.0 * M_PI * (c + f.xq[q]) * g.h) * f.wq[q] * g.h;
+        for (int i = 0; i < f.n; ++i)
+          r1[c * g.k + i] += f.B[q * f.n + i] * s;
+      }
+  if (int e = upload_tab(ctx, r1))
+    return e;
+  VEC_LAUNCH(k_outer_product, g.N, g, ctx->d_tab, 1.0, 1, r);
+  return SPIRK_OK;
+}
+
+int spirk_problem_interpolate_solution(spirk_ctx *ctx, const spirk_level *lvl, double *u, double t)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo           g = make_geo(lvl);
+  const Fe1D         &f = g_fe[g.k];
+  std::vector<double> s1(g.n1);
+  for (int c = 0; c < g.nc; ++c)
+    for (int i = 0; i < f.n; ++i)
+      s1[c * g.k + i] = std::sin(2.0 * M_PI * (c + f.nodes[i]) * g.h);
+  if (int e = upload_tab(ctx, s1))
+    return e;
+  const double ft = (1.0 + std::sin(M_PI * t)) * std::exp(-0.5 * t);
+  VEC_LAUNCH(k_outer_product, g.N, g, ctx->d_tab, ft, 0, u);
+  return SPIRK_OK;
+}
+
+int spirk_problem_error_norms(spirk_ctx *ctx, const spirk_level *lvl, const double *u, double t, double *l2, double *linf)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo    g  = make_geo(lvl);
+  const double ft = (1.0 + std::sin(M_PI * t)) * std::exp(-0.5 * t);
+  SPIRK_CUDA(cudaMemsetAsync(ctx->d_result, 0, 2 * sizeof(double), ctx->stream));
+  const long long ncells = (g.dim == 3) ? (long long)g.nc * g.nc * g.nc : (long long)g.nc * g.nc;
+  const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 8);
+  if (g.dim == 3)
+    {
+      SPIRK_DISPATCH_K(g.k, (k_error_norms<K, 3><<<grid, 128, 0, ctx->stream>>>(g, u, ft, ctx->d_result)));
+    }
+  else
+    {
+      SPIRK_DISPATCH_K(g.k, (k_error_norms<K, 2><<<grid, 128, 0, ctx->stream>>>(g, u, ft, ctx->d_result)));
+    }
+  SPIRK_LAUNCH_CHECK(ctx);
+  SPIRK_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  *l2   = std::sqrt(ctx->h_result[0]);
+  *linf = ctx->h_result[1];
+  return SPIRK_OK;
+}
+
+int spirk_constraints_set_zero(spirk_ctx *ctx, const spirk_level *lvl, int nb, double *u, long long stride)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo g = make_geo(lvl);
+  VEC_LAUNCH(k_set_zero_bdry, g.N * nb, g, nb, u, stride);
+  return SPIRK_OK;
+}
+
+// ------------------------------------------------------------------------------- NCCL
+int spirk_comm_unique_id(char *id128)
+{
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  SPIRK_NCCL(nccl.GetUniqueId(&id));
+  std::memcpy(id128, &id, 128);
+  return SPIRK_OK;
+}
+int spirk_comm_create(spirk_ctx *ctx, const char *id128, int n_ranks, int rank, spirk_comm **out)
+{
+  SPIRK_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  spirk_comm *c = new spirk_comm();
+  c->rank = rank, c->n_ranks = n_ranks;
+  const NcclApi &api = nccl_api();
+  if (!api.ok)
+    {
+      delete c;
+      return set_error(SPIRK_ERR_COMM, api.error);
+    }
+  ncclResult_t r = api.CommInitRank(&c->comm, n_ranks, id, rank);
+  if (r != ncclSuccess)
+    {
+      delete c;
+      return set_error(SPIRK_ERR_COMM, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
+    }
+  *out = c;
+  return SPIRK_OK;
+}
+int spirk_comm_destroy(spirk_comm *c)
+{
+  if (c)
+    {
+      if (c->comm && nccl_api().ok)
+        nccl_api().CommDestroy(c->comm);
+      delete c;
+    }
+  return SPIRK_OK;
+}
+int spirk_comm_rank(const spirk_comm *c, int *rank, int *n)
+{
+  *rank = c->rank, *n = c->n_ranks;
+  return SPIRK_OK;
+}
+int spirk_comm_allreduce_sum(spirk_ctx *ctx, spirk_comm *c, double *buf, long long n)
+{
+  if (c->n_ranks == 1)
+    return SPIRK_OK;
+  SPIRK_NCCL(nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, c->comm, ctx->stream));
+  ctx->launches++;
+  return SPIRK_OK;
+}
+int spirk_comm_allgather(spirk_ctx *ctx, spirk_comm *c, double *recv, const double *send, long long n)
+{
+  if (c->n_ranks == 1)
+    {
+      if (recv != send)
+        SPIRK_CUDA(cudaMemcpyAsync(recv, send, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+      return SPIRK_OK;
+    }
+  SPIRK_NCCL(nccl.AllGather(send, recv, n, ncclDouble, c->comm, ctx->stream));
+  ctx->launches++;
+  return SPIRK_OK;
+}
+int spirk_ctx_set_reduction_comm(spirk_ctx *ctx, spirk_comm *comm)
+{
+  ctx->reduction_comm = comm;
+  return SPIRK_OK;
+}
+}

@@ -1,0 +1,198 @@
+/*
+ * spirk_b200.h — C ABI of the B200-native device layer for the dealii-spirk hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / PODs and returns an int
+ * status (SPIRK_OK == 0); nothing throws across this boundary and no torch / C++ type appears
+ * in a signature.  All `double*` vector arguments are DEVICE pointers obtained from
+ * spirk_malloc unless the name says `host`.  All work is enqueued on the context's stream;
+ * only functions that return a scalar to the host (dot products, norms) and spirk_ctx_sync
+ * synchronise.
+ *
+ * The library that ships (dealii_spirk_b200/libspirk_b200.so) implements this header with
+ * hand-written sm_100a CUDA kernels and fails loudly without a GPU.  A second, TEST-ONLY
+ * implementation of the same header on the CPU lives in oracle/cpu_abi.cc (the "port" oracle).
+ *
+ * Each group cites the reference interface it replaces (paths relative to the reference root).
+ *
+ * Data layout: the mesh is the r-times refined unit hypercube with FE_Q(k); DoFs are numbered
+ * lexicographically, index = ix + n1*(iy + n1*iz), n1 = k*2^r + 1.  A "block vector" with nb
+ * blocks is nb such arrays at a common stride (>= n_dofs) from a base pointer.
+ */
+#ifndef SPIRK_B200_H
+#define SPIRK_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPIRK_MAX_BLOCKS 16
+
+enum
+{
+  SPIRK_OK              = 0,
+  SPIRK_ERR_INVALID     = 1, /* bad argument */
+  SPIRK_ERR_DEVICE      = 2, /* CUDA runtime error (or: no GPU) */
+  SPIRK_ERR_NOMEM       = 3,
+  SPIRK_ERR_UNSUPPORTED = 4, /* dim / degree / feature not compiled */
+  SPIRK_ERR_COMM        = 5  /* NCCL error */
+};
+
+typedef struct spirk_ctx  spirk_ctx;  /* one per host thread / GPU: device, stream, scratch */
+typedef struct spirk_comm spirk_comm; /* NCCL communicator wrapper */
+
+/* Mesh level: replaces what MatrixFree<dim,double>::reinit(MappingQ1, dof_handler, constraints,
+ * QGauss(k+1)) stores for the hypercube (operator.h:254-269, main.cc:3038-3039, 3109-3144). */
+typedef struct
+{
+  int dim;        /* 2 or 3 */
+  int degree;     /* k = 1..6 */
+  int n_cells_1d; /* 2^r */
+  int reserved;
+} spirk_level;
+
+/* Operator descriptor.  dst_i = laplace[i] * K src_i + M * sum_j coupling[i*nb+j] src_j on
+ * unconstrained DoFs, dst_i = src_i on Dirichlet DoFs.
+ *   kind REAL     : coupling ignored, diagonal mass[i]      (MassLaplaceOperatorMatrixFree::vmult,
+ *                   operator.h:298-310,379-421; Batched...::vmult, operator.h:811-880)
+ *   kind COUPLED  : full coupling matrix (IRK SystemMatrix main.cc:1014-1028 fused into one cell
+ *                   pass; complex pair operator.h:616-665 with coupling [[lre,-lim],[lim,lre]]) */
+typedef struct
+{
+  int    kind; /* SPIRK_OP_REAL / SPIRK_OP_COUPLED */
+  int    nb;   /* number of blocks, 1..SPIRK_MAX_BLOCKS */
+  double mass[SPIRK_MAX_BLOCKS];
+  double laplace[SPIRK_MAX_BLOCKS];
+  double coupling[SPIRK_MAX_BLOCKS * SPIRK_MAX_BLOCKS];
+} spirk_opdesc;
+
+enum
+{
+  SPIRK_OP_REAL    = 0,
+  SPIRK_OP_COUPLED = 1
+};
+
+/* ---- library / context ------------------------------------------------------------------ */
+const char *spirk_backend(void);    /* "cuda-sm_100a" for the product library */
+const char *spirk_last_error(void); /* message of the last non-OK status on this thread */
+int         spirk_ctx_create(spirk_ctx **ctx, int device);
+int         spirk_ctx_destroy(spirk_ctx *ctx);
+int         spirk_ctx_sync(spirk_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long spirk_ctx_launch_count(spirk_ctx *ctx);
+/* CUDA-event timing on the context's stream: begin/end return elapsed milliseconds */
+int spirk_ctx_timer_begin(spirk_ctx *ctx);
+int spirk_ctx_timer_end(spirk_ctx *ctx, double *ms);
+/* kernel variant selection for A/B tests: 0 = default (fastest validated), see DESIGN.md */
+int spirk_ctx_set_option(spirk_ctx *ctx, const char *name, int value);
+
+/* ---- memory (replaces LinearAlgebra::distributed::Vector storage, main.cc:67-68) --------- */
+int spirk_malloc(spirk_ctx *ctx, double **ptr, size_t n);
+int spirk_free(spirk_ctx *ctx, double *ptr);
+int spirk_copy_h2d(spirk_ctx *ctx, double *dst, const double *host_src, size_t n);
+int spirk_copy_d2h(spirk_ctx *ctx, double *host_dst, const double *src, size_t n);
+/* pinned host staging buffers for the end-to-end path */
+int spirk_malloc_host(spirk_ctx *ctx, double **ptr, size_t n);
+int spirk_free_host(spirk_ctx *ctx, double *ptr);
+
+long long spirk_level_n_dofs(const spirk_level *lvl);
+
+/* ---- matrix-free operator (operator.h:250-460, 529-698, 749-881) ------------------------- */
+/* dst = A src */
+int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst,
+                   const double *src, long long stride);
+/* dst = rhs - A src  (Multigrid::level_v_step residual, MGSmootherPrecondition::smooth) */
+int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst,
+                      const double *rhs, const double *src, long long stride);
+/* one Chebyshev iteration (deal.II PreconditionChebyshev, preconditioner.h:353-373):
+ *   x_new = x + f1[b] (x - x_old) + f2[b] dinv .* (rhs - A x);  x_old == NULL means x_old = 0 */
+int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op,
+                       double *x_new, const double *x, const double *x_old, const double *rhs,
+                       const double *dinv, long long stride, const double *f1, const double *f2);
+/* inverse diagonal of mass*M + laplace*K: abs(d) > 1e-10 ? 1/d : 1, Dirichlet entries 1
+ * (operator.h:361-373, 560-575, 775-792) */
+int spirk_op_inverse_diagonal(spirk_ctx *ctx, const spirk_level *lvl, double *diag, double mass,
+                              double laplace);
+/* dense matrix of mass*M + laplace*K (+ identity rows on Dirichlet DoFs) for tiny levels,
+ * row-major n x n on the HOST; replaces get_system_matrix(), operator.h:331-353 */
+int spirk_op_assemble_dense(spirk_ctx *ctx, const spirk_level *lvl, double mass, double laplace,
+                            double *host_matrix);
+
+/* ---- multigrid transfer (MGTwoLevelTransfer, preconditioner.h:266-282) ------------------- */
+/* fine += P coarse (coarse Dirichlet DoFs read as 0); lvl_fine.n_cells_1d must be even */
+int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lvl_fine, int nb, double *fine,
+                            long long fine_stride, const double *coarse, long long coarse_stride);
+/* coarse = P^T fine, coarse Dirichlet DoFs set to 0 */
+int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lvl_fine, int nb, double *coarse,
+                      long long coarse_stride, const double *fine, long long fine_stride);
+/* y_b = Minv x_b for tiny dense coarse problems (n x n row-major DEVICE matrix); replaces the
+ * Trilinos-ML coarse solve on the one-cell level, preconditioner.h:375-406 */
+int spirk_dense_matvec(spirk_ctx *ctx, int n, int nb, double *y, const double *x, long long stride,
+                       const double *matrix);
+
+/* ---- vector kernels (deal.II Vector ops used by SolverCG / SolverGMRES / Chebyshev and the
+ *      integrators; list in SURVEY 8b "Vector API the callers use") ------------------------ */
+int spirk_vec_set(spirk_ctx *ctx, double *x, long long n, double value);
+int spirk_vec_copy(spirk_ctx *ctx, double *dst, const double *src, long long n);
+int spirk_vec_scale(spirk_ctx *ctx, double *x, long long n, double a);                 /* x *= a */
+int spirk_vec_axpy(spirk_ctx *ctx, double *y, double a, const double *x, long long n); /* y += a x */
+/* y = s*y + a*x   (sadd) */
+int spirk_vec_sadd(spirk_ctx *ctx, double *y, double s, double a, const double *x, long long n);
+/* y += a*x + b*z  (add(a,V,b,W), main.cc:2221-2224) */
+int spirk_vec_add2(spirk_ctx *ctx, double *y, double a, const double *x, double b, const double *z,
+                   long long n);
+/* y = a*x (equ) */
+int spirk_vec_equ(spirk_ctx *ctx, double *y, double a, const double *x, long long n);
+/* y_b = f[b] * d_b .* x_b  (Chebyshev iteration 0) */
+int spirk_vec_scale_pointwise(spirk_ctx *ctx, int nb, long long n, double *y, const double *d,
+                              const double *x, long long stride, const double *f);
+/* reductions: result written to HOST (synchronises).  If a reduction communicator is attached to
+ * the context (spirk_ctx_set_reduction_comm) the value is all-reduced over it first, which is
+ * what ReshapedVector does over the row communicator (main.cc:237-264). */
+int spirk_vec_dot(spirk_ctx *ctx, const double *x, const double *y, long long n, double *host_result);
+/* v += a*V; result = v . W   (add_and_dot) */
+int spirk_vec_add_and_dot(spirk_ctx *ctx, double *v, double a, const double *V, const double *W,
+                          long long n, double *host_result);
+int spirk_vec_sum(spirk_ctx *ctx, const double *x, long long n, double *host_result);
+/* modified Gram-Schmidt sweep of SolverGMRES in one call:
+ *   h[0] = vv.q0; h[i] = (vv -= h[i-1] q_{i-1}).q_i; norm = sqrt((vv -= h[dim-1] q_{dim-1}).vv)
+ * basis vector i lives at basis + i*basis_stride; h (dim) and norm are HOST outputs */
+int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *basis, long long basis_stride, int dim,
+                    long long n, double *host_h, double *host_norm);
+/* stage mixing dst_i = [dst_i +] sum_j T[i*q_in+j] src_j, skipping |T_ij| <= cutoff
+ * (main.cc:1100-1104, 1164-1168, 877-891, 1511-1529); T is a HOST row-major q_out x q_in matrix */
+int spirk_mix(spirk_ctx *ctx, int q_out, int q_in, double *dst, long long dst_stride,
+              const double *src, long long src_stride, long long n, const double *host_T, int add,
+              double cutoff);
+
+/* ---- problem pieces (main.cc:3213-3219, 3301-3307, 3355, 3436-3469, 3495-3602) ----------- */
+/* r_i = int phi_i(x) sin(2 pi x)sin(2 pi y)[sin(2 pi z)] dx with QGauss(k+1); Dirichlet entries 0.
+ * create_right_hand_side(t) = g(t) * r because the forcing is separable (main.cc:3523-3539). */
+int spirk_problem_rhs_spatial(spirk_ctx *ctx, const spirk_level *lvl, double *r);
+/* nodal interpolation of the analytical solution at time t (main.cc:3570-3594) */
+int spirk_problem_interpolate_solution(spirk_ctx *ctx, const spirk_level *lvl, double *u, double t);
+/* L2 and Linf error against the analytical solution with QGauss(k+2) (main.cc:3436-3469) */
+int spirk_problem_error_norms(spirk_ctx *ctx, const spirk_level *lvl, const double *u, double t,
+                              double *host_l2, double *host_linf);
+/* AffineConstraints::set_zero / distribute for homogeneous Dirichlet (main.cc:3307, 3355) */
+int spirk_constraints_set_zero(spirk_ctx *ctx, const spirk_level *lvl, int nb, double *u,
+                               long long stride);
+
+/* ---- communication (replaces the MPI call sites listed in SURVEY 2.3) -------------------- */
+int spirk_comm_unique_id(char *id128); /* 128 bytes */
+int spirk_comm_create(spirk_ctx *ctx, const char *id128, int n_ranks, int rank, spirk_comm **comm);
+int spirk_comm_destroy(spirk_comm *comm);
+int spirk_comm_rank(const spirk_comm *comm, int *rank, int *n_ranks);
+/* in-place sum over the communicator (MPI_Allreduce, main.cc:1421-1426, 241-263) */
+int spirk_comm_allreduce_sum(spirk_ctx *ctx, spirk_comm *comm, double *buf, long long n);
+/* recv[r*n .. r*n+n) = send of rank r (replaces the MPI_Sendrecv_replace ring, main.cc:1465-1483) */
+int spirk_comm_allgather(spirk_ctx *ctx, spirk_comm *comm, double *recv, const double *send,
+                         long long n);
+/* attach / detach (NULL) the communicator over which dot products are summed */
+int spirk_ctx_set_reduction_comm(spirk_ctx *ctx, spirk_comm *comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPIRK_B200_H */

@@ -840,8 +840,12 @@ def direct_irk_step(prob, q, tau, u, time):
     Ku = K @ ui
     g = np.stack([prob.rhs(time + (c[i] - 1.0) * tau)[inner].reshape(-1) - Ku for i in range(q)])
     rhs = (A_inv @ g).reshape(-1)
-    S = (sp.kron(sp.csr_matrix(A_inv), M) + tau * sp.kron(sp.identity(q), K)).tocsc()
-    ksol = spla.splu(S).solve(rhs).reshape(q, -1)
+    key = ("lu", q, tau)
+    cache = prob.__dict__.setdefault("_direct_cache", {})
+    if key not in cache:  # the stage matrix does not change between steps
+        S = (sp.kron(sp.csr_matrix(A_inv), M) + tau * sp.kron(sp.identity(q), K)).tocsc()
+        cache[key] = spla.splu(S)
+    ksol = cache[key].solve(rhs).reshape(q, -1)
     unew = u.copy()
     ni = n1 - 2
     unew[inner] = (ui + tau * (b @ ksol)).reshape((1,) + (ni,) * dim)

@@ -1,0 +1,284 @@
+"""Checks of any implementation of include/spirk_b200.h against the NumPy oracle.
+
+The same functions run in the CPU suite against the CPU double (oracle/_build/libspirk_cpu.so)
+and in the `-m gpu` suite against the product CUDA library through the C ABI.
+Tolerances: FP64, relative 1e-12 per kernel application (north_star asks 1e-10 on the solution).
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import spirk_oracle as so  # noqa: E402
+from dealii_spirk_b200 import capi  # noqa: E402
+
+RTOL = 1e-12
+
+
+def synth(n, seed=0):
+    """stateless synthetic vector of SURVEY 8(d): 2*frac(sin(12.9898*(i+1))*43758.5453)-1."""
+    i = np.arange(n, dtype=np.float64) + 1.0 + 1000.0 * seed
+    v = np.sin(12.9898 * i) * 43758.5453
+    return 2.0 * (v - np.floor(v)) - 1.0
+
+
+def relerr(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def make_level(dim, k, r):
+    return capi.Level(dim, k, 2 ** r, 0), so.Level(dim, k, r)
+
+
+def block_input(olv, nb, seed=0, zero_boundary=False):
+    u = synth(nb * olv.N, seed).reshape((nb,) + olv.shape)
+    if zero_boundary:
+        u[:, olv.bmask] = 0.0
+    return u
+
+
+def check_op_apply(dev, dim, k, r, desc, tol=RTOL):
+    """desc: ('real', mass[], lap[]) or ('coupled', C[][], lap[])."""
+    lvl, olv = make_level(dim, k, r)
+    if desc[0] == "real":
+        op = capi.real_op(desc[1], desc[2])
+        mass = np.atleast_1d(np.asarray(desc[1], float))
+        nb = len(mass)
+        lap = np.broadcast_to(np.atleast_1d(np.asarray(desc[2], float)), (nb,))
+        u = block_input(olv, nb, seed=1)
+        ref = olv.apply(u, mass, lap)
+    else:
+        Cm = np.asarray(desc[1], float)
+        nb = Cm.shape[0]
+        lap = np.broadcast_to(np.atleast_1d(np.asarray(desc[2], float)), (nb,))
+        op = capi.coupled_op(Cm, lap)
+        u = block_input(olv, nb, seed=2)
+        v = u.copy()
+        v[:, olv.bmask] = 0.0
+        Mv = olv.apply(v, 1.0, 0.0)
+        Kv = olv.apply(v, 0.0, lap)
+        ref = Kv + np.tensordot(Cm, Mv, axes=(1, 0))
+        ref[:, olv.bmask] = u[:, olv.bmask]
+    with capi.Context(dev) as ctx:
+        src = ctx.upload(u)
+        dst = ctx.alloc(u.size)
+        ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, olv.N)
+        out = ctx.download(dst, u.shape)
+    e = relerr(out, ref)
+    assert e < tol, f"op_apply {desc[0]} dim={dim} k={k} r={r}: rel err {e}"
+    return e
+
+
+def check_residual_and_cheb(dev, dim, k, r, nb=2):
+    lvl, olv = make_level(dim, k, r)
+    mass = np.array([16.0, 3.1618475338398158, 2.9418686642961562, 5.644106850167844][:nb])
+    lap = np.full(nb, 0.1)
+    op = capi.real_op(mass, lap)
+    x = block_input(olv, nb, 3, True)
+    xo = block_input(olv, nb, 4, True)
+    b = block_input(olv, nb, 5, True)
+    dinv = np.concatenate([olv.inverse_diagonal(m, 0.1) for m in mass])
+    Ax = olv.apply(x, mass, lap)
+    f1 = np.array([0.3, 0.2, 0.25, 0.35][:nb])
+    f2 = np.array([1.1, 0.9, 1.0, 1.2][:nb])
+    bc = (slice(None),) + (None,) * dim
+    with capi.Context(dev) as ctx:
+        dx, dxo, db, dd = (ctx.upload(a) for a in (x, xo, b, dinv))
+        dres, dnew = ctx.alloc(x.size), ctx.alloc(x.size)
+        ctx.call("spirk_op_residual", C.byref(lvl), C.byref(op), dres, db, dx, olv.N)
+        res = ctx.download(dres, x.shape)
+        assert relerr(res, b - Ax) < RTOL
+        pf1, _a = capi.darr(f1)
+        pf2, _b = capi.darr(f2)
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dnew, dx, dxo, db, dd, olv.N, pf1, pf2)
+        new = ctx.download(dnew, x.shape)
+        ref = x + f1[bc] * (x - xo) + f2[bc] * dinv * (b - Ax)
+        assert relerr(new, ref) < RTOL
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dnew, dx, None, db, dd, olv.N, pf1, pf2)
+        new = ctx.download(dnew, x.shape)
+        ref = (1 + f1[bc]) * x + f2[bc] * dinv * (b - Ax)
+        assert relerr(new, ref) < RTOL
+
+
+def check_inverse_diagonal(dev, dim, k, r, mass=16.0, lap=0.1):
+    lvl, olv = make_level(dim, k, r)
+    with capi.Context(dev) as ctx:
+        d = ctx.alloc(olv.N)
+        ctx.call("spirk_op_inverse_diagonal", C.byref(lvl), d, mass, lap)
+        out = ctx.download(d, (1,) + olv.shape)
+    assert relerr(out, olv.inverse_diagonal(mass, lap)) < RTOL
+
+
+def check_assemble_dense(dev, dim, k):
+    lvl, olv = make_level(dim, k, 0)
+    N = olv.N
+    with capi.Context(dev) as ctx:
+        A = np.zeros((N, N))
+        ctx.call("spirk_op_assemble_dense", C.byref(lvl), 3.0, 0.1, A.ctypes.data_as(C.c_void_p))
+    ref = np.zeros((N, N))
+    for j in range(N):
+        e = np.zeros(N)
+        e[j] = 1
+        ref[:, j] = olv.apply(e.reshape((1,) + olv.shape), 3.0, 0.1).reshape(-1)
+    assert relerr(A, ref) < RTOL
+
+
+def check_transfer(dev, dim, k, r, nb=2):
+    lvl, olv = make_level(dim, k, r)
+    g = so.GMG(dim, k, r, lambda lv: so.ScalarOp(lv))
+    olc = g.levels[r - 1]
+    uc = block_input(olc, nb, 6)
+    uf0 = block_input(olv, nb, 7)
+    uf = block_input(olv, nb, 8)
+    with capi.Context(dev) as ctx:
+        dc, df = ctx.upload(uc), ctx.upload(uf0)
+        ctx.call("spirk_mg_prolongate_add", C.byref(lvl), nb, df, olv.N, dc, olc.N)
+        out = ctx.download(df, uf0.shape)
+        assert relerr(out, uf0 + g.prolongate(r, uc)) < RTOL
+        df2, dc2 = ctx.upload(uf), ctx.alloc(uc.size)
+        ctx.call("spirk_mg_restrict", C.byref(lvl), nb, dc2, olc.N, df2, olv.N)
+        out = ctx.download(dc2, uc.shape)
+        assert relerr(out, g.restrict(r, uf)) < RTOL
+
+
+def check_vector_ops(dev, n=100003):
+    x, y, z = synth(n, 1), synth(n, 2), synth(n, 3)
+    with capi.Context(dev) as ctx:
+        dx, dy, dz = ctx.upload(x), ctx.upload(y), ctx.upload(z)
+        assert abs(ctx.scalar_call("spirk_vec_dot", dx, dy, n) - x @ y) < 1e-10 * n ** 0.5
+        assert abs(ctx.scalar_call("spirk_vec_sum", dx, n) - x.sum()) < 1e-10 * n ** 0.5
+        ctx.call("spirk_vec_axpy", dy, 0.5, dx, n)
+        y = y + 0.5 * x
+        ctx.call("spirk_vec_sadd", dy, 2.0, -1.5, dz, n)
+        y = 2.0 * y - 1.5 * z
+        ctx.call("spirk_vec_add2", dy, 0.25, dx, -0.75, dz, n)
+        y = y + 0.25 * x - 0.75 * z
+        ctx.call("spirk_vec_scale", dy, n, 1.25)
+        y = 1.25 * y
+        assert relerr(ctx.download(dy, (n,)), y) < 1e-14
+        r = ctx.scalar_call("spirk_vec_add_and_dot", dy, -0.3, dx, dz, n)
+        y = y - 0.3 * x
+        assert abs(r - y @ z) < 1e-10 * n ** 0.5
+        assert relerr(ctx.download(dy, (n,)), y) < 1e-14
+        ctx.call("spirk_vec_equ", dz, 3.0, dx, n)
+        assert relerr(ctx.download(dz, (n,)), 3.0 * x) < 1e-15
+        ctx.call("spirk_vec_copy", dz, dy, n)
+        assert np.array_equal(ctx.download(dz, (n,)), ctx.download(dy, (n,)))
+        ctx.call("spirk_vec_set", dz, n, 0.0)
+        assert ctx.scalar_call("spirk_vec_dot", dz, dz, n) == 0.0
+        # pointwise
+        nb, m = 3, n // 3
+        f = np.array([0.5, 2.0, -1.0])
+        pf, _ = capi.darr(f)
+        ctx.call("spirk_vec_scale_pointwise", nb, m, dz, dx, dy, m, pf)
+        ref = (f[:, None] * (x[:nb * m].reshape(nb, m) * y[:nb * m].reshape(nb, m))).reshape(-1)
+        assert relerr(ctx.download(dz, (nb * m,)), ref) < 1e-14
+
+
+def check_mgs(dev, n=50021, dim=5):
+    rng = np.random.default_rng(1)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, dim)))
+    basis = np.ascontiguousarray(Q.T)
+    vv = synth(n, 9)
+    h = np.zeros(dim)
+    w = vv.copy()
+    for i in range(dim):
+        h[i] = w @ basis[i]
+        w = w - h[i] * basis[i]
+    with capi.Context(dev) as ctx:
+        dv, db = ctx.upload(vv), ctx.upload(basis)
+        hh = np.zeros(dim)
+        nrm = C.c_double()
+        ctx.call("spirk_gmres_mgs", dv, db, n, dim, n, hh.ctypes.data_as(capi.dp), C.byref(nrm))
+        out = ctx.download(dv, (n,))
+    assert np.max(np.abs(hh - h)) < 1e-11 * np.linalg.norm(vv)
+    assert abs(nrm.value - np.linalg.norm(w)) < 1e-11 * np.linalg.norm(vv)
+    assert relerr(out, w) < 1e-12
+
+
+def check_mix(dev, q=4, n=20011):
+    T = so.table("T_inv", q)
+    src = synth(q * n, 4).reshape(q, n)
+    dst0 = synth(q * n, 5).reshape(q, n)
+    pT, _ = capi.darr(T)
+    with capi.Context(dev) as ctx:
+        ds, dd = ctx.upload(src), ctx.upload(dst0)
+        ctx.call("spirk_mix", q, q, dd, n, ds, n, n, pT, 0, 1e-12)
+        assert relerr(ctx.download(dd, (q, n)), so.mix(T, src)) < 1e-13
+        ctx.call("spirk_vec_copy", dd, ctx.upload(dst0), q * n)
+        ctx.call("spirk_mix", q, q, dd, n, ds, n, n, pT, 1, 1e-12)
+        assert relerr(ctx.download(dd, (q, n)), dst0 + so.mix(T, src)) < 1e-13
+        # rectangular: 1 x q (update u += tau * b^T k)
+        b = so.table("b_vec_", q)
+        pb, _ = capi.darr(0.1 * b)
+        du = ctx.upload(dst0[0])
+        ctx.call("spirk_mix", 1, q, du, n, ds, n, n, pb, 1, 0.0)
+        assert relerr(ctx.download(du, (n,)), dst0[0] + 0.1 * (b @ src)) < 1e-13
+
+
+def check_problem(dev, dim, k, r):
+    lvl, olv = make_level(dim, k, r)
+    prob = so.Problem(dim, k, r)
+    with capi.Context(dev) as ctx:
+        d = ctx.alloc(olv.N)
+        ctx.call("spirk_problem_rhs_spatial", C.byref(lvl), d)
+        assert relerr(ctx.download(d, (1,) + olv.shape), prob.rspace) < 1e-12
+        ctx.call("spirk_problem_interpolate_solution", C.byref(lvl), d, 0.3)
+        u = ctx.download(d, (1,) + olv.shape)
+        assert relerr(u, prob.exact_nodal(0.3)) < 1e-12
+        l2, li = C.c_double(), C.c_double()
+        ctx.call("spirk_problem_error_norms", C.byref(lvl), d, 0.3, C.byref(l2), C.byref(li))
+        e = prob.errors(u, 0.3)
+        assert abs(l2.value - e[0]) < 1e-9 * e[0] and abs(li.value - e[1]) < 1e-9 * e[1]
+        ctx.call("spirk_constraints_set_zero", C.byref(lvl), 1, d, olv.N)
+        u2 = ctx.download(d, (1,) + olv.shape)
+        assert np.all(u2[:, olv.bmask] == 0.0) and np.array_equal(u2[:, ~olv.bmask], u[:, ~olv.bmask])
+
+
+def check_dense_matvec(dev, n=27, nb=3):
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((n, n))
+    x = rng.standard_normal((nb, 40))
+    with capi.Context(dev) as ctx:
+        dA, dx, dy = ctx.upload(A), ctx.upload(x), ctx.alloc(nb * 40)
+        ctx.call("spirk_dense_matvec", n, nb, dy, dx, 40, dA)
+        y = ctx.download(dy, (nb, 40))
+    assert relerr(y[:, :n], x[:, :n] @ A.T) < 1e-13
+
+
+D4 = [16.0, 3.1618475338398158, 2.9418686642961562, 5.644106850167844]
+OP_CASES = [
+    ("real", [16.0], [0.1]),
+    ("real", [1.0], [0.0]),
+    ("real", [0.0], [-1.0]),
+    ("real", D4, [0.1]),
+    ("coupled", [[5.0, 3.0], [-3.0, 5.0]], [0.1]),                       # complex pair
+    ("coupled", so.table("A_inv", 4).tolist(), [0.1]),                    # IRK system matrix
+]
+
+
+def run_all(dev, small=True):
+    for case in OP_CASES:
+        check_op_apply(dev, 3, 4, 1 if small else 3, case)
+    check_op_apply(dev, 2, 2, 3, OP_CASES[0])
+    check_op_apply(dev, 2, 4, 2, OP_CASES[3])
+    check_op_apply(dev, 3, 1, 2, OP_CASES[0])
+    check_op_apply(dev, 3, 2, 2, OP_CASES[4])
+    check_op_apply(dev, 3, 3, 1, OP_CASES[0])
+    check_residual_and_cheb(dev, 3, 4, 1)
+    check_residual_and_cheb(dev, 2, 2, 3, nb=1)
+    for (dim, k, r) in [(3, 4, 1), (2, 2, 3), (3, 1, 2)]:
+        check_inverse_diagonal(dev, dim, k, r)
+        check_transfer(dev, dim, k, r)
+        check_problem(dev, dim, k, r)
+    check_assemble_dense(dev, 3, 4)
+    check_assemble_dense(dev, 2, 2)
+    check_vector_ops(dev)
+    check_mgs(dev)
+    check_mix(dev)
+    check_dense_matvec(dev)

@@ -1,0 +1,45 @@
+"""-m gpu: every kernel of the CUDA library, called through the C ABI, against the NumPy oracle."""
+import pytest
+
+import abi_checks as ac
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", range(len(ac.OP_CASES)))
+def test_op_apply_3d_q4(gpu_dev, case):
+    ac.check_op_apply(gpu_dev, 3, 4, 2, ac.OP_CASES[case])
+
+
+@pytest.mark.parametrize("dim,k,r", [(2, 1, 3), (2, 2, 3), (2, 3, 2), (2, 4, 2), (2, 5, 2), (2, 6, 1),
+                                     (3, 1, 3), (3, 2, 2), (3, 3, 2), (3, 5, 1), (3, 6, 1), (3, 4, 0), (3, 4, 1),
+                                     (3, 4, 3)])
+def test_op_apply_shapes(gpu_dev, dim, k, r):
+    ac.check_op_apply(gpu_dev, dim, k, r, ac.OP_CASES[0])
+    ac.check_op_apply(gpu_dev, dim, k, r, ac.OP_CASES[3])
+    ac.check_op_apply(gpu_dev, dim, k, r, ac.OP_CASES[4])
+
+
+@pytest.mark.parametrize("dim,k,r,nb", [(3, 4, 2, 2), (3, 4, 1, 4), (2, 2, 3, 1), (3, 1, 3, 2)])
+def test_residual_and_chebyshev_step(gpu_dev, dim, k, r, nb):
+    ac.check_residual_and_cheb(gpu_dev, dim, k, r, nb)
+
+
+@pytest.mark.parametrize("dim,k,r", [(3, 4, 2), (2, 2, 4), (3, 1, 3), (3, 2, 2), (2, 4, 2)])
+def test_diag_transfer_problem(gpu_dev, dim, k, r):
+    ac.check_inverse_diagonal(gpu_dev, dim, k, r)
+    ac.check_transfer(gpu_dev, dim, k, r)
+    ac.check_problem(gpu_dev, dim, k, r)
+
+
+def test_assemble_dense(gpu_dev):
+    ac.check_assemble_dense(gpu_dev, 3, 4)
+    ac.check_assemble_dense(gpu_dev, 2, 2)
+
+
+def test_vector_kernels(gpu_dev):
+    ac.check_vector_ops(gpu_dev)
+    ac.check_mgs(gpu_dev)
+    ac.check_mix(gpu_dev)
+    ac.check_mix(gpu_dev, q=8)
+    ac.check_dense_matvec(gpu_dev)
