@@ -1,0 +1,293 @@
+#!/usr/bin/env python3
+"""Benchmark of the dealii-spirk hot path on B200 (contract: see the task statement / DESIGN.md).
+
+A "step" is one fully implicit Runge-Kutta time step of the 3-D Q4 heat equation (rhs assembly,
+GMG-preconditioned GMRES on the stage system, solution update).
+
+  N = 1 : BASELINE.json configs[1]: 3-D Q4, IRK q=2, GMG preconditioner, single B200
+  N > 1 : stage-parallel SPIRK with q = N stages, one Radau-IIA stage per GPU (configs[2] at N=4,
+          configs[4]'s q=8 at N=8), NCCL all-gather stage mixing + all-reduced Krylov scalars.
+
+metric  : stage-DoFs advanced per second = n_dofs * q / (time per step)   [GDoF*stage/s];
+          ms_per_step is the time per SPIRK step; the roofline object reports the dominant kernel
+          (the fused Chebyshev cell-operator step) as algorithmic bytes / CUDA-event time against the
+          measured HBM copy bandwidth; `vmult_gdofs` is the plain stage-vmult throughput.
+value   : device-resident (solution stays in HBM between steps);   e2e: the same step through the
+          host-buffer entry point (H2D of u_n from pinned memory + solve + D2H of u_{n+1}).
+
+`--impl reference` times the CPU restatement of the reference (oracle/cpu_abi.cc behind the same
+C++ host layer, OpenMP on all host cores) on a bounded sample (smaller refinement) of the workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+TABLES = os.path.join(ROOT, "dealii_spirk_b200", "tables", "butcher_tables.txt")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--refine", type=int, default=6, help="global refinements r: n_dofs = (4*2^r+1)^3")
+    ap.add_argument("--degree", type=int, default=4)
+    ap.add_argument("--stages", type=int, default=0, help="RK stages q (default: 2 at N=1, N otherwise)")
+    ap.add_argument("--scheme", default="", help="irk | spirk | irk_batched | complex_* (default irk at N=1, spirk else)")
+    ap.add_argument("--outer-tolerance", type=float, default=1e-8, help="reference default main.cc:2964")
+    ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def params(scheme, k, r, q, tol, n_steps):
+    return {"FEDegree": k, "NRefinements": r, "TimeIntegrationScheme": scheme, "IRKStages": q, "TimeStepSize": 0.1,
+            "EndTime": 0.1 * n_steps + 0.05, "OperatorType": "MatrixFree", "BlockPreconditionerType": "GMG",
+            "OuterTolerance": tol, "InnerTolerance": 0.0, "DoOutputParaview": False}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.proc = index, [], set(), None
+        self.max_mhz = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            return
+        threading.Thread(target=self._read, daemon=True).start()
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_run(a, q, scheme, n_steps, warmup):
+    """the restated reference algorithm on the host cores (bounded sample: refinement a.cpu_refine)"""
+    from dealii_spirk_b200 import hostapi
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
+    host = hostapi.HostLib(os.path.join(ROOT, "oracle", "_build", "libspirk_host_cpu.so"), TABLES)
+    cores = os.cpu_count() or 1
+    r = a.cpu_refine
+    with hostapi.Run(host, params(scheme, a.degree, r, q, a.outer_tolerance, n_steps + warmup), dim=3) as run:
+        run.set_compute_errors(False)
+        run.setup()
+        n = run.scalar("n_dofs")
+        for _ in range(warmup):
+            run.step()
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            run.step()
+        dt = (time.perf_counter() - t0) / n_steps
+        outer = run.array("outer_iterations")
+    return {"value": n * q / dt * 1e-9, "ms_per_step": dt * 1e3, "cores": cores, "n_dofs": int(n), "refine": r,
+            "outer_iterations": outer.tolist()}
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = a.gpus
+    q = a.stages or (2 if n_gpus == 1 else n_gpus)
+    scheme = a.scheme or ("irk" if n_gpus == 1 else "spirk")
+    metric = "implicit RK time step: stage-DoFs advanced per second (n_dofs*q/step time); ms_per_step = time per SPIRK step"
+    unit = "GDoF*stage/s"
+    config = {"workload": f"3D heat equation Q{a.degree}, {scheme} q={q}, GMG(Chebyshev 5)+GMRES, hypercube r={a.refine}",
+              "n_dofs": (a.degree * 2 ** a.refine + 1) ** 3, "stages": q, "refine": a.refine, "degree": a.degree,
+              "outer_tolerance": a.outer_tolerance, "dt": 0.1,
+              "parallelism": "1 GPU, stages batched" if n_gpus == 1 else f"stage-parallel: {q // n_gpus} stage(s) per GPU x {n_gpus}",
+              "l2_policy": "working set (>= 30 vectors of n_dofs*8 B) exceeds the 126 MB L2; no explicit flush"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        ref = cpu_reference_run(a, q, "irk" if scheme == "spirk" else scheme, max(1, min(a.steps, 3)), 1)
+        sample = f"same scheme/q/degree at refinement r={ref['refine']} ({ref['n_dofs']} DoFs), {ref['cores']} OpenMP threads"
+        line = {"impl": "reference", "metric": metric, "value": ref["value"], "unit": unit, "n_gpus": n_gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ref["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": ref["value"], "unit": unit, "cores": ref["cores"], "kind": "port", "sample": sample},
+                "e2e": {"value": ref["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "restated reference algorithm (cell-loop sum factorisation, deal.II conventions), not deal.II itself"}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import dealii_spirk_b200 as pkg
+    from dealii_spirk_b200 import capi, hostapi
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = pkg.device_lib()
+    host = hostapi.HostLib(pkg.HOST_LIB_PATH, TABLES)
+    if host.backend() != "cuda-sm_100a":
+        raise SystemExit("the product host library must be linked against the CUDA device library")
+
+    nccl_id = None
+    if world > 1:
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            dev.call("spirk_comm_unique_id", buf)
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        nccl_id = bytes(t.cpu().numpy().tobytes())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    total_steps = 2 * (a.steps + a.warmup) + 2
+    run = hostapi.Run(host, params(scheme, a.degree, a.refine, q, a.outer_tolerance, total_steps), dim=3, device=local_rank,
+                      nccl_id=nccl_id, rank=rank, world=world)
+    run.setup()
+    n_dofs = run.scalar("n_dofs")
+    err0 = run.array("error_L2")
+    run.set_compute_errors(False)  # the QGauss(k+2) error evaluation is output, not part of solve()
+
+    sampler = ClockSampler(local_rank)
+    # ---- device-resident steps
+    for _ in range(a.warmup):
+        run.step()
+    barrier()
+    l0 = run.scalar("launch_count")
+    sampler.start()
+    # CUDA events on the library's own stream (torch.cuda.Event would only see torch's stream)
+    run.timer_begin()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        run.step()
+    dev_ms = run.timer_end()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = run.scalar("launch_count") - l0
+    step_seconds = run.array("step_seconds")[-a.steps:]
+    t_step = max_over_ranks(dev_ms * 1e-3 / a.steps)
+    outer = run.array("outer_iterations")[-a.steps:]
+
+    # ---- end-to-end steps through host buffers (pinned staging inside the library call)
+    u_pin = torch.empty(int(n_dofs), dtype=torch.float64, pin_memory=True)  # pinned host staging
+    u_host = u_pin.numpy()
+    u_host[:] = run.solution()
+    for _ in range(max(1, a.warmup // 2)):
+        run.step_host(u_host)
+    barrier()
+    run.timer_begin()
+    for _ in range(a.steps):
+        run.step_host(u_host)
+    t_e2e = max_over_ranks(run.timer_end() * 1e-3 / a.steps)
+    barrier()
+    clocks = sampler.stop()
+    run.set_compute_errors(True)
+    run.step()
+    err_final = run.array("error_L2")[-1]
+
+    # ---- dominant kernel, timed live with CUDA events on the library's stream
+    roof, vmult_gdofs = None, None
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        lvl = capi.Level(3, a.degree, 2 ** a.refine, 0)
+        N = lvl.n_dofs
+        m = q if n_gpus == 1 else q // n_gpus
+        with capi.Context(dev, local_rank) as ctx:
+            x, xo, rhs, dinv, dst = (ctx.alloc(m * N) for _ in range(5))
+            ctx.call("spirk_vec_set", x, m * N, 0.5)
+            ctx.call("spirk_op_inverse_diagonal", C.byref(lvl), dinv, 16.0, 0.1)
+            op = capi.real_op([16.0, 3.16, 2.94, 5.64, 1.0, 2.0, 3.0, 4.0][:m], [0.1])
+            f1, _k1 = capi.darr([0.3] * m)
+            f2, _k2 = capi.darr([1.1] * m)
+            res = {}
+            for name, fn in (("cheb_step", lambda: ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dst, x, xo, rhs,
+                                                            dinv, N, f1, f2)),
+                             ("vmult", lambda: ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, x, N))):
+                for _ in range(3):
+                    fn()
+                reps = 20
+                ctx.call("spirk_ctx_timer_begin")
+                for _ in range(reps):
+                    fn()
+                res[name] = ctx.scalar_call("spirk_ctx_timer_end") / reps
+        # algorithmic bytes per DoF*stage: fused Chebyshev step reads x, x_old, rhs, dinv and
+        # writes x_new = 40 B; plain vmult reads src, writes dst = 16 B
+        cheb_gbs = 40.0 * m * N / res["cheb_step"] * 1e-6
+        vmult_gdofs = m * N / res["vmult"] * 1e-6
+        roof = {"bound": "hbm", "kernel": "fused Chebyshev step (cell operator + 3-term update), the smoother's kernel",
+                "achieved": cheb_gbs, "peak": peak, "unit": "GB/s", "frac": cheb_gbs / peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_dof": 40, "launch_ms": res["cheb_step"],
+                "vmult": {"achieved": 16.0 * vmult_gdofs, "frac": 16.0 * vmult_gdofs / peak, "launch_ms": res["vmult"],
+                          "algorithmic_bytes_per_dof": 16}}
+    run.close()
+
+    cpu = None
+    if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
+        ref = cpu_reference_run(a, q, scheme, 2, 1)
+        cpu = {"value": ref["value"], "unit": unit, "cores": ref["cores"], "kind": "port",
+               "sample": f"same scheme/q/degree at r={ref['refine']} ({ref['n_dofs']} DoFs), 2 timed steps, "
+                         f"{ref['cores']} OpenMP threads; restated reference algorithm, not deal.II",
+               "ms_per_step": ref["ms_per_step"]}
+
+    if rank == 0:
+        value = n_dofs * q / t_step * 1e-9
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config, "clocks": clocks,
+                "e2e": {"value": n_dofs * q / t_e2e * 1e-9, "unit": unit, "ms_per_step": t_e2e * 1e3,
+                        "h2d_bytes_per_step": int(n_dofs * 8), "d2h_bytes_per_step": int(n_dofs * 8)},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "vmult_gdofs": vmult_gdofs,
+                "outer_iterations": [int(x) for x in outer], "step_ms_host_clock": [round(s * 1e3, 3) for s in step_seconds], "wall_ms_per_step": wall / a.steps * 1e3,
+                "error_L2_t0": float(err0[0]), "error_L2_final": float(err_final)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

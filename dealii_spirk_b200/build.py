@@ -54,9 +54,12 @@ def build_host(force=False):
     srcs = [s for s in host_sources() if os.path.exists(s)]
     if not force and not _newer(HOST_LIB, srcs + [DEVICE_LIB]):
         return HOST_LIB
-    ccs = [s for s in srcs if s.endswith(".cc")]
-    _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-I" + os.path.join(ROOT, "include"), "-o", HOST_LIB]
-         + ccs + ["-L" + HERE, "-lspirk_b200", "-Wl,-rpath,$ORIGIN"])
+    inc = "-I" + os.path.join(ROOT, "include")
+    _run([GXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-reorder", "-Wno-comment", inc, "-o", HOST_LIB,
+          os.path.join(HERE, "host", "host_capi.cc"), "-L" + HERE, "-lspirk_b200", "-Wl,-rpath,$ORIGIN"])
+    # stand-alone driver with the reference's command line (main.cc:3608-3791)
+    _run([GXX, "-O2", "-std=c++17", inc, "-o", os.path.join(HERE, "spirk_main"), os.path.join(HERE, "host", "main.cc"),
+          "-L" + HERE, "-lspirk_host", "-lspirk_b200", "-Wl,-rpath,$ORIGIN"])
     return HOST_LIB
 
 

@@ -65,6 +65,10 @@ _SIGS = {
     "spirk_ctx_timer_begin": [C.c_void_p],
     "spirk_ctx_timer_end": [C.c_void_p, dp],
     "spirk_ctx_set_option": [C.c_void_p, C.c_char_p, C.c_int],
+    "spirk_graph_begin": [C.c_void_p],
+    "spirk_graph_end": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "spirk_graph_launch": [C.c_void_p, C.c_void_p],
+    "spirk_graph_destroy": [C.c_void_p],
     "spirk_malloc": [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t],
     "spirk_free": [C.c_void_p, C.c_void_p],
     "spirk_copy_h2d": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
@@ -81,7 +85,7 @@ _SIGS = {
     "spirk_mg_prolongate_add": [C.c_void_p, C.POINTER(Level), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
                                 C.c_longlong],
     "spirk_mg_restrict": [C.c_void_p, C.POINTER(Level), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong],
-    "spirk_dense_matvec": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p],
+    "spirk_dense_matvec": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong],
     "spirk_vec_set": [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double],
     "spirk_vec_copy": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong],
     "spirk_vec_scale": [C.c_void_p, C.c_void_p, C.c_longlong, C.c_double],
@@ -94,7 +98,7 @@ _SIGS = {
     "spirk_vec_dot": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, dp],
     "spirk_vec_add_and_dot": [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_longlong, dp],
     "spirk_vec_sum": [C.c_void_p, C.c_void_p, C.c_longlong, dp],
-    "spirk_gmres_mgs": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, dp, dp],
+    "spirk_gmres_mgs": [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_longlong, dp, dp],
     "spirk_mix": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong,
                   dp, C.c_int, C.c_double],
     "spirk_problem_rhs_spatial": [C.c_void_p, C.POINTER(Level), C.c_void_p],

@@ -165,10 +165,11 @@ namespace spirk
 
   // y_b = A x_b, tiny dense (coarse-grid solve): one block per vector block
   __global__ void k_dense_matvec(const int n, double *__restrict__ y, const double *__restrict__ x, const long long stride,
-                                 const double *__restrict__ A)
+                                 const double *__restrict__ A0, const long long matrix_stride)
   {
     extern __shared__ double sx[];
     const int                b = blockIdx.x;
+    const double            *A = A0 + b * matrix_stride;
     for (int j = threadIdx.x; j < n; j += blockDim.x)
       sx[j] = x[b * stride + j];
     __syncthreads();

@@ -301,6 +301,53 @@ int spirk_ctx_set_option(spirk_ctx *ctx, const char *name, int value)
   return set_error(SPIRK_ERR_INVALID, std::string("unknown option ") + name);
 }
 
+// ------------------------------------------------------------------------------- graphs
+struct spirk_graph
+{
+  cudaGraph_t     graph = nullptr;
+  cudaGraphExec_t exec  = nullptr;
+};
+int spirk_graph_begin(spirk_ctx *ctx)
+{
+  SPIRK_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  return SPIRK_OK;
+}
+int spirk_graph_end(spirk_ctx *ctx, spirk_graph **out)
+{
+  spirk_graph *g = new spirk_graph();
+  cudaError_t  e = cudaStreamEndCapture(ctx->stream, &g->graph);
+  if (e == cudaSuccess)
+    e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess)
+    {
+      if (g->graph)
+        cudaGraphDestroy(g->graph);
+      delete g;
+      cudaGetLastError();
+      return set_error(SPIRK_ERR_DEVICE, std::string("graph capture: ") + cudaGetErrorString(e));
+    }
+  *out = g;
+  return SPIRK_OK;
+}
+int spirk_graph_launch(spirk_ctx *ctx, spirk_graph *g)
+{
+  SPIRK_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+  ctx->launches++;
+  return SPIRK_OK;
+}
+int spirk_graph_destroy(spirk_graph *g)
+{
+  if (g)
+    {
+      if (g->exec)
+        cudaGraphExecDestroy(g->exec);
+      if (g->graph)
+        cudaGraphDestroy(g->graph);
+      delete g;
+    }
+  return SPIRK_OK;
+}
+
 int spirk_malloc(spirk_ctx *ctx, double **ptr, size_t n)
 {
   (void)ctx;
@@ -517,11 +564,12 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
   return SPIRK_OK;
 }
 
-int spirk_dense_matvec(spirk_ctx *ctx, int n, int nb, double *y, const double *x, long long stride, const double *matrix)
+int spirk_dense_matvec(spirk_ctx *ctx, int n, int nb, double *y, const double *x, long long stride, const double *matrix,
+                       long long matrix_stride)
 {
   if (n < 1 || n > 4096 || y == x)
     return set_error(SPIRK_ERR_INVALID, "dense_matvec: bad size or aliasing");
-  k_dense_matvec<<<nb, 128, n * sizeof(double), ctx->stream>>>(n, y, x, stride, matrix);
+  k_dense_matvec<<<nb, 128, n * sizeof(double), ctx->stream>>>(n, y, x, stride, matrix, matrix_stride);
   SPIRK_LAUNCH_CHECK(ctx);
   return SPIRK_OK;
 }
@@ -614,18 +662,17 @@ int spirk_vec_sum(spirk_ctx *ctx, const double *x, long long n, double *host_res
   return finish_reduction(ctx, 1, grid, host_result);
 }
 
-int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *basis, long long bs, int dim, long long n, double *h,
-                    double *norm)
+int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *const *basis, int dim, long long n, double *h, double *norm)
 {
   if (dim < 1)
     return set_error(SPIRK_ERR_INVALID, "gmres_mgs: dim");
-  if (int e = spirk_vec_dot(ctx, vv, basis, n, &h[0]))
+  if (int e = spirk_vec_dot(ctx, vv, basis[0], n, &h[0]))
     return e;
   for (int i = 1; i < dim; ++i)
-    if (int e = spirk_vec_add_and_dot(ctx, vv, -h[i - 1], basis + (i - 1) * bs, basis + i * bs, n, &h[i]))
+    if (int e = spirk_vec_add_and_dot(ctx, vv, -h[i - 1], basis[i - 1], basis[i], n, &h[i]))
       return e;
   double s = 0;
-  if (int e = spirk_vec_add_and_dot(ctx, vv, -h[dim - 1], basis + (dim - 1) * bs, vv, n, &s))
+  if (int e = spirk_vec_add_and_dot(ctx, vv, -h[dim - 1], basis[dim - 1], vv, n, &s))
     return e;
   *norm = std::sqrt(s);
   return SPIRK_OK;

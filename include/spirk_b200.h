@@ -87,6 +87,15 @@ int spirk_ctx_timer_end(spirk_ctx *ctx, double *ms);
 /* kernel variant selection for A/B tests: 0 = default (fastest validated), see DESIGN.md */
 int spirk_ctx_set_option(spirk_ctx *ctx, const char *name, int value);
 
+/* CUDA-graph capture of a launch sequence that contains no host synchronisation (the V-cycle):
+ * begin -> enqueue kernels through this API -> end returns a replayable graph.  Returns
+ * SPIRK_ERR_UNSUPPORTED where capture is not available (the caller then replays eagerly). */
+typedef struct spirk_graph spirk_graph;
+int spirk_graph_begin(spirk_ctx *ctx);
+int spirk_graph_end(spirk_ctx *ctx, spirk_graph **graph);
+int spirk_graph_launch(spirk_ctx *ctx, spirk_graph *graph);
+int spirk_graph_destroy(spirk_graph *graph);
+
 /* ---- memory (replaces LinearAlgebra::distributed::Vector storage, main.cc:67-68) --------- */
 int spirk_malloc(spirk_ctx *ctx, double **ptr, size_t n);
 int spirk_free(spirk_ctx *ctx, double *ptr);
@@ -129,7 +138,7 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lvl_fine, int nb, doubl
 /* y_b = Minv x_b for tiny dense coarse problems (n x n row-major DEVICE matrix); replaces the
  * Trilinos-ML coarse solve on the one-cell level, preconditioner.h:375-406 */
 int spirk_dense_matvec(spirk_ctx *ctx, int n, int nb, double *y, const double *x, long long stride,
-                       const double *matrix);
+                       const double *matrix, long long matrix_stride /* 0: one matrix for all blocks */);
 
 /* ---- vector kernels (deal.II Vector ops used by SolverCG / SolverGMRES / Chebyshev and the
  *      integrators; list in SURVEY 8b "Vector API the callers use") ------------------------ */
@@ -157,9 +166,9 @@ int spirk_vec_add_and_dot(spirk_ctx *ctx, double *v, double a, const double *V, 
 int spirk_vec_sum(spirk_ctx *ctx, const double *x, long long n, double *host_result);
 /* modified Gram-Schmidt sweep of SolverGMRES in one call:
  *   h[0] = vv.q0; h[i] = (vv -= h[i-1] q_{i-1}).q_i; norm = sqrt((vv -= h[dim-1] q_{dim-1}).vv)
- * basis vector i lives at basis + i*basis_stride; h (dim) and norm are HOST outputs */
-int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *basis, long long basis_stride, int dim,
-                    long long n, double *host_h, double *host_norm);
+ * host_basis[i] is the DEVICE pointer of basis vector i; h (dim) and norm are HOST outputs */
+int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *const *host_basis, int dim, long long n,
+                    double *host_h, double *host_norm);
 /* stage mixing dst_i = [dst_i +] sum_j T[i*q_in+j] src_j, skipping |T_ij| <= cutoff
  * (main.cc:1100-1104, 1164-1168, 877-891, 1511-1529); T is a HOST row-major q_out x q_in matrix */
 int spirk_mix(spirk_ctx *ctx, int q_out, int q_in, double *dst, long long dst_stride,

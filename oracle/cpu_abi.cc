@@ -458,6 +458,15 @@ int spirk_ctx_timer_end(spirk_ctx *ctx, double *ms)
 }
 int spirk_ctx_set_option(spirk_ctx *, const char *, int) { return SPIRK_OK; }
 
+struct spirk_graph
+{
+  int dummy;
+};
+int spirk_graph_begin(spirk_ctx *) { return fail(SPIRK_ERR_UNSUPPORTED, "no graph capture on the CPU double"); }
+int spirk_graph_end(spirk_ctx *, spirk_graph **) { return fail(SPIRK_ERR_UNSUPPORTED, "no graph capture"); }
+int spirk_graph_launch(spirk_ctx *, spirk_graph *) { return fail(SPIRK_ERR_UNSUPPORTED, "no graph capture"); }
+int spirk_graph_destroy(spirk_graph *) { return SPIRK_OK; }
+
 int spirk_malloc(spirk_ctx *, double **ptr, size_t n)
 {
   *ptr = (double *)std::calloc(n ? n : 1, sizeof(double));
@@ -709,14 +718,15 @@ int spirk_mg_restrict(spirk_ctx *, const spirk_level *lf, int nb, double *coarse
   return SPIRK_OK;
 }
 
-int spirk_dense_matvec(spirk_ctx *, int n, int nb, double *y, const double *x, long long stride, const double *matrix)
+int spirk_dense_matvec(spirk_ctx *, int n, int nb, double *y, const double *x, long long stride, const double *matrix,
+                       long long matrix_stride)
 {
   for (int b = 0; b < nb; ++b)
     for (int i = 0; i < n; ++i)
       {
         double s = 0;
         for (int j = 0; j < n; ++j)
-          s += matrix[(size_t)i * n + j] * x[b * stride + j];
+          s += matrix[b * matrix_stride + (size_t)i * n + j] * x[b * stride + j];
         y[b * stride + i] = s;
       }
   return SPIRK_OK;
@@ -799,15 +809,14 @@ int spirk_vec_sum(spirk_ctx *, const double *x, long long n, double *r)
   *r = s;
   return SPIRK_OK;
 }
-int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *basis, long long bs, int dim, long long n, double *h,
-                    double *norm)
+int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *const *basis, int dim, long long n, double *h, double *norm)
 {
-  spirk_vec_dot(ctx, vv, basis, n, &h[0]);
+  spirk_vec_dot(ctx, vv, basis[0], n, &h[0]);
   for (int i = 1; i < dim; ++i)
-    spirk_vec_add_and_dot(ctx, vv, -h[i - 1], basis + (i - 1) * bs, basis + i * bs, n, &h[i]);
+    spirk_vec_add_and_dot(ctx, vv, -h[i - 1], basis[i - 1], basis[i], n, &h[i]);
   double s;
   // vv.add_and_dot(-h(dim-1), q_{dim-1}, vv)
-  spirk_vec_axpy(ctx, vv, -h[dim - 1], basis + (dim - 1) * bs, n);
+  spirk_vec_axpy(ctx, vv, -h[dim - 1], basis[dim - 1], n);
   spirk_vec_dot(ctx, vv, vv, n, &s);
   *norm = std::sqrt(s);
   return SPIRK_OK;

@@ -194,7 +194,8 @@ def check_mgs(dev, n=50021, dim=5):
         dv, db = ctx.upload(vv), ctx.upload(basis)
         hh = np.zeros(dim)
         nrm = C.c_double()
-        ctx.call("spirk_gmres_mgs", dv, db, n, dim, n, hh.ctypes.data_as(capi.dp), C.byref(nrm))
+        ptrs = (C.c_void_p * dim)(*[db.value + 8 * n * i for i in range(dim)])
+        ctx.call("spirk_gmres_mgs", dv, ptrs, dim, n, hh.ctypes.data_as(capi.dp), C.byref(nrm))
         out = ctx.download(dv, (n,))
     assert np.max(np.abs(hh - h)) < 1e-11 * np.linalg.norm(vv)
     assert abs(nrm.value - np.linalg.norm(w)) < 1e-11 * np.linalg.norm(vv)
@@ -246,9 +247,14 @@ def check_dense_matvec(dev, n=27, nb=3):
     x = rng.standard_normal((nb, 40))
     with capi.Context(dev) as ctx:
         dA, dx, dy = ctx.upload(A), ctx.upload(x), ctx.alloc(nb * 40)
-        ctx.call("spirk_dense_matvec", n, nb, dy, dx, 40, dA)
+        ctx.call("spirk_dense_matvec", n, nb, dy, dx, 40, dA, 0)
         y = ctx.download(dy, (nb, 40))
-    assert relerr(y[:, :n], x[:, :n] @ A.T) < 1e-13
+        assert relerr(y[:, :n], x[:, :n] @ A.T) < 1e-13
+        As = rng.standard_normal((nb, n, n))
+        dAs = ctx.upload(As)
+        ctx.call("spirk_dense_matvec", n, nb, dy, dx, 40, dAs, n * n)
+        y = ctx.download(dy, (nb, 40))
+        assert relerr(y[:, :n], np.einsum("bij,bj->bi", As, x[:, :n])) < 1e-13
 
 
 D4 = [16.0, 3.1618475338398158, 2.9418686642961562, 5.644106850167844]

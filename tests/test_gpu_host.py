@@ -1,0 +1,58 @@
+"""-m gpu: the product stack (CUDA kernels + C++ host layer) through the host C API, against the
+NumPy oracle.  Same bars as the CPU suite: solution / error norms 1e-10, iteration counts +-1."""
+import numpy as np
+import pytest
+
+import host_checks as hc
+from dealii_spirk_b200 import hostapi
+import dealii_spirk_b200 as pkg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu_host():
+    pkg.device_lib()
+    host = hostapi.HostLib(pkg.HOST_LIB_PATH, hc.TABLES)
+    assert host.backend() == "cuda-sm_100a"
+    return host
+
+
+CASES = [
+    ("irk", 2, 2, 3, 2), ("irk", 3, 4, 2, 4), ("irk", 3, 4, 3, 2), ("spirk", 3, 4, 2, 4), ("irk_batched", 3, 4, 2, 4),
+    ("complex_irk", 3, 4, 2, 4), ("complex_irk_batched", 3, 4, 2, 4), ("complex_spirk", 2, 2, 3, 3),
+    ("complex_spirk_batched", 3, 4, 1, 8), ("ost", 2, 2, 5, 0), ("irk", 3, 1, 3, 2), ("spirk", 3, 4, 2, 8),
+]
+
+
+@pytest.mark.parametrize("scheme,dim,k,r,q", CASES)
+def test_scheme_matches_oracle(gpu_host, scheme, dim, k, r, q):
+    # q = 8: attainable accuracy of the stage vectors is ~1e-10 (cond(T) = 7e5)
+    hc.compare(gpu_host, scheme, dim, k, r, q, sol_tol=1e-10 if q < 8 else 1e-9)
+
+
+def test_inner_tolerance_path(gpu_host):
+    hc.compare(gpu_host, "irk", 2, 2, 3, 2, inner=1e-6)
+
+
+def test_end_to_end_host_buffers(gpu_host):
+    """the reference-facing call with HOST buffers: Interface::solve on a host solution vector"""
+    p = hc.params("irk", 4, 2, 2)
+    with hostapi.Run(gpu_host, p, dim=3) as a, hostapi.Run(gpu_host, p, dim=3) as b:
+        a.setup(), b.setup()
+        u = b.solution()
+        for _ in range(3):
+            a.step()
+            b.step_host(u)
+        assert np.array_equal(a.solution(), u)
+
+
+def test_manufactured_solution_full_size(gpu_host):
+    """size-independent property at a BASELINE size (3-D Q4 r=5, 2.1e6 DoFs): the error against the
+    analytical solution stays at the spatial discretisation level h^(k+1) and matches r=4 / 32."""
+    errs = {}
+    for r in (4, 5):
+        res = hc.run_host(gpu_host, "irk", 3, 4, r, 2, tol=1e-10, end=0.2)
+        errs[r] = res["error_L2"][-1]
+        assert np.all(res["outer"] <= 8)
+    assert errs[5] < errs[4] / 8.0
