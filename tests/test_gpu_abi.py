@@ -20,7 +20,8 @@ def test_op_apply_shapes(gpu_dev, dim, k, r):
     ac.check_op_apply(gpu_dev, dim, k, r, ac.OP_CASES[4])
 
 
-@pytest.mark.parametrize("dim,k,r,nb", [(3, 4, 2, 2), (3, 4, 1, 4), (2, 2, 3, 1), (3, 1, 3, 2)])
+@pytest.mark.parametrize("dim,k,r,nb", [(3, 4, 2, 2), (3, 4, 1, 4), (2, 2, 3, 1), (3, 1, 3, 2), (3, 4, 3, 2), (3, 4, 4, 1),
+                                        (3, 4, 3, 4)])
 def test_residual_and_chebyshev_step(gpu_dev, dim, k, r, nb):
     ac.check_residual_and_cheb(gpu_dev, dim, k, r, nb)
 
@@ -30,6 +31,30 @@ def test_diag_transfer_problem(gpu_dev, dim, k, r):
     ac.check_inverse_diagonal(gpu_dev, dim, k, r)
     ac.check_transfer(gpu_dev, dim, k, r)
     ac.check_problem(gpu_dev, dim, k, r)
+
+
+@pytest.mark.parametrize("r", [3, 4, 5])
+def test_fast_path_matches_general_kernel(gpu_dev, r):
+    """variant 2 (fused, tile columns) against variant 1 (general cell kernel) and the oracle"""
+    import ctypes as C
+    import numpy as np
+    from dealii_spirk_b200 import capi
+    lvl, olv = ac.make_level(3, 4, r)
+    u = ac.block_input(olv, 2, seed=11)
+    op = capi.real_op([16.0, 2.9418686642961562], [0.1])
+    outs = []
+    with capi.Context(gpu_dev) as ctx:
+        src, dst = ctx.upload(u), ctx.alloc(u.size)
+        for variant in (1, 0):
+            ctx.call("spirk_ctx_set_option", b"apply_variant", variant)
+            ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, olv.N)
+            outs.append(ctx.download(dst, u.shape))
+        ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, olv.N)
+        again = ctx.download(dst, u.shape)
+    assert ac.relerr(outs[0], outs[1]) < 1e-13
+    assert np.array_equal(outs[1], again), "variant 2 must be bitwise reproducible (no atomics)"
+    if r <= 4:
+        assert ac.relerr(outs[1], olv.apply(u, [16.0, 2.9418686642961562], [0.1, 0.1])) < 1e-12
 
 
 def test_assemble_dense(gpu_dev):

@@ -44,7 +44,8 @@ def test_end_to_end_host_buffers(gpu_host):
         for _ in range(3):
             a.step()
             b.step_host(u)
-        assert np.array_equal(a.solution(), u)
+        ua = a.solution()
+        assert np.max(np.abs(ua - u)) <= 1e-11 * np.max(np.abs(u))
 
 
 def test_manufactured_solution_full_size(gpu_host):
