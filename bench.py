@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--outer-tolerance", type=float, default=1e-8, help="reference default main.cc:2964")
     ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="bracket the timed device-resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -197,11 +199,15 @@ def main():
     l0 = run.scalar("launch_count")
     sampler.start()
     # CUDA events on the library's own stream (torch.cuda.Event would only see torch's stream)
+    if a.profile:
+        torch.cuda.profiler.start()
     run.timer_begin()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         run.step()
     dev_ms = run.timer_end()
+    if a.profile:
+        torch.cuda.profiler.stop()
     barrier()
     wall = time.perf_counter() - t0
     launches = run.scalar("launch_count") - l0

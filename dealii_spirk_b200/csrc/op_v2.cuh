@@ -30,6 +30,9 @@
 //   operator.h:298-310, 379-421 (vmult), 841-880 (batched); deal.II PreconditionChebyshev
 //   vector_updates and the residual of Multigrid::level_v_step (A8).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+
 #include "op_v1.cuh"
 
 namespace spirk
@@ -44,16 +47,26 @@ namespace spirk
   template <int K, int TX, int TY>
   struct CfgV2
   {
-    static constexpr int n = K + 1, LX = K * TX + 1, LY = K * TY + 1, PL = LX * LY;
-    static constexpr int itemsA = TX * LY * n, itemsB = LX * TY * n, itemsC = PL;
-    static constexpr int IPT = 2; // work items per thread and layer (keeps the register tiles spill-free)
-    static constexpr int TA = (((itemsA + IPT - 1) / IPT + 31) / 32) * 32, TB = (((itemsB + IPT - 1) / IPT + 31) / 32) * 32,
-                         TC = (((itemsC + IPT - 1) / IPT + 31) / 32) * 32;
-    static constexpr int TD      = 128; // epilogue / store warps
+    static constexpr int n = K + 1, LX = K * TX + 1, LY = K * TY + 1;
+    static constexpr int LXP = LX + 1;     // padded row pitch (even: 16-byte aligned rows for 128-bit LDS/STS)
+    static constexpr int PLP = LXP * LY;   // padded plane
+    static constexpr int NPG = (n + 1) / 2; // plane groups: a thread of group A/B owns <= 2 planes of its line
+    static constexpr int pairsA = TX * LY, pairsB = LX * TY;
+    static constexpr int TA = ((pairsA * NPG + 31) / 32) * 32, TB = ((pairsB * NPG + 31) / 32) * 32;
+    static constexpr int TC = (((LX * LY + 2) / 3 + 31) / 32) * 32; // three node columns per thread
+    static constexpr int TD = 320;                                 // epilogue / store warps
     static constexpr int threads = TA + TB + TC + TD;
-    static constexpr int ring    = 2 * K + 1; // node planes of the current layer + the K new planes of the next one
-    static constexpr size_t smem = sizeof(double) * (ring + 8 * n + 2 * K) * PL; // ring + 2 x (A,B) + 2 x (S,P) + 2 x OUT
+    static constexpr int ringp   = 3 * K; // node-plane ring: 3 layers x K planes
+    // epilogue operands staged per layer: none (apply), rhs (residual), rhs + dinv + src + x_old (Chebyshev)
+    __host__ __device__ static constexpr int nops(const int mode) { return mode == 2 ? 4 : (mode == 1 ? 1 : 0); }
+    static constexpr int NE_D = (K * (LX - 2) * (LY - 2) + TD - 1) / TD + (K * (2 * LX + 2 * (LY - 2)) + TD - 1) / TD;
+    // ring + 2 x (A,B) + 2 x (S,P) + 2 x OUT + thread-private (E, F) slots of the epilogue group
+    static constexpr size_t smem(const int mode)
+    {
+      return sizeof(double) * ((size_t)(ringp + 8 * n + 2 * K) * PLP + (nops(mode) > 0 ? 2 * (size_t)NE_D * TD : 0));
+    }
     static_assert(threads <= 1024, "tile too large for one CTA");
+    static_assert(K % 2 == 0, "128-bit shared accesses need an even degree");
   };
 
   struct V2Args
@@ -96,14 +109,14 @@ namespace spirk
   __global__ void __launch_bounds__(CfgV2<K, TX, TY>::threads, 1) k_v2_main(const V2Args a)
   {
     using C             = CfgV2<K, TX, TY>;
-    constexpr int n = C::n, LX = C::LX, LY = C::LY, PL = C::PL, RING = C::ring, IPT = C::IPT;
+    constexpr int n = C::n, LX = C::LX, LY = C::LY, LXP = C::LXP, PLP = C::PLP, NPG = C::NPG;
     constexpr int TA = C::TA, TB = C::TB, TC = C::TC, TD = C::TD;
-    constexpr int NPF = (K * PL + TA - 1) / TA; // prefetch elements per group-A thread and layer
     // named barriers (0 is __syncthreads)
     constexpr int BAR_AB_FULL = 1, BAR_AB_EMPTY = 3, BAR_SP_FULL = 5, BAR_SP_EMPTY = 7, BAR_A = 9, BAR_OUT_FULL = 10,
                   BAR_OUT_EMPTY = 12;
-    extern __shared__ double sm[];
-    double *U = sm, *AB = sm + RING * PL, *SP = AB + 4 * n * PL, *OUT = SP + 4 * n * PL; // AB[buf][A|B][plane], SP[buf][S|P][plane], OUT[buf][plane]
+    extern __shared__ __align__(16) double sm[];
+    // U: ring of 3 layers x K node planes; AB[buf][A|B][plane]; SP[buf][S|P][plane]; OUT[buf][plane < K]
+    double *U = sm, *AB = sm + C::ringp * PLP, *SP = AB + 4 * n * PLP, *OUT = SP + 4 * n * PLP;
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
 
     const int n1 = a.g.n1, nc = a.g.nc;
@@ -120,53 +133,56 @@ namespace spirk
     const int       z_first = (zb > 0 ? zb - 1 : zb), n_layers = ze - z_first;
     const long long boff = (long long)b * a.stride, plane = (long long)n1 * n1;
     const double   *src  = a.src + boff;
-
     if (threadIdx.x < TA)
       {
         // =========================== group A: staging + x-lines ===========================
-        const int t = threadIdx.x;
-        // prefetch descriptors of the K new planes of a layer: element e = t + i*TA
-        const double *pf_base = src + plane * ((long long)K * (z_first + 1));
-        int           pf_off[NPF], pf_goff[NPF];
+        const int  t    = threadIdx.x;
+        const int  pair = t % C::pairsA, pg = t / C::pairsA;
+        const int  seg  = pair % TX, off = (pair / TX) * LXP + K * seg;
+        const bool act  = pg < NPG;
+        // prefetch descriptors of the K new planes of a layer: element e = t + i*TA of K x (LX x LY)
+        constexpr int NPF = (K * LX * LY + TA - 1) / TA;
+        int           pf_s[NPF], pf_g[NPF]; // smem offset (bit 30: x/y Dirichlet, bit 29: top plane of the layer); global offset
 #pragma unroll
         for (int i = 0; i < NPF; ++i)
           {
             const int e = t + i * TA;
-            const int X = e % LX, Y = (e / LX) % LY, pl = 1 + e / PL;
+            const int X = e % LX, Y = (e / LX) % LY, pl = 1 + e / (LX * LY);
             const int gx = gx0 + X, gy = gy0 + Y;
-            pf_off[i]  = (e < K * PL) ? (Y * LX + X) | (pl << 16) | ((on_bdry(gx, n1) || on_bdry(gy, n1)) ? (1 << 30) : 0) : -1;
-            pf_goff[i] = gx + n1 * gy + (int)plane * pl;
+            pf_g[i] = gx + n1 * gy + (int)plane * pl;
+            pf_s[i] = (e < K * LX * LY) ? ((pl == K ? 0 : pl * PLP) + Y * LXP + X) | (pl == K ? (1 << 29) : 0) |
+                                            ((on_bdry(gx, n1) || on_bdry(gy, n1)) ? (1 << 30) : 0)
+                                        : -1;
           }
-        // prologue: all k+1 planes of the first layer
-        for (int e = t; e < n * PL; e += TA)
+        // prologue: all k+1 planes of the first layer -> ring groups 0 (planes 0..K-1) and 1 (plane K)
+        for (int e = t; e < n * LX * LY; e += TA)
           {
-            const int  X = e % LX, Y = (e / LX) % LY, gz = K * z_first + e / PL;
+            const int  X = e % LX, Y = (e / LX) % LY, pl = e / (LX * LY), gz = K * z_first + pl;
             const int  gx = gx0 + X, gy = gy0 + Y;
             const bool bd = on_bdry(gx, n1) || on_bdry(gy, n1) || on_bdry(gz, n1);
-            const unsigned int sp = (unsigned int)__cvta_generic_to_shared(U + (gz % RING) * PL + Y * LX + X);
+            const unsigned int sp = (unsigned int)__cvta_generic_to_shared(U + pl * PLP + Y * LXP + X);
             const int          sz = bd ? 0 : 8;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sp), "l"(src + gx + (long long)n1 * gy + plane * gz), "r"(sz));
           }
         asm volatile("cp.async.commit_group;\n" ::);
-        int slot0 = (K * z_first) % RING; // ring slot of plane 0 of the current layer
+        const double *pf_base = src + plane * ((long long)K * (z_first + 1)); // plane 0 of the next layer
+        int           cur = 0, nxt = K * PLP, nn = 2 * K * PLP;                  // ring group bases (elements)
         for (int it = 0; it < n_layers; ++it)
           {
             asm volatile("cp.async.wait_all;\n" ::);
             bar_sync(BAR_A, TA); // this layer's planes are visible to group A; layer it-1 is fully consumed
             if (it + 1 < n_layers)
               {
+                const bool top = (z_first + it + 2 == nc); // plane K of the next layer is the Dirichlet top plane
 #pragma unroll
                 for (int i = 0; i < NPF; ++i)
-                  if (pf_off[i] >= 0)
+                  if (pf_s[i] >= 0)
                     {
-                      const int pl = (pf_off[i] >> 16) & 15;
-                      const int gz = K * (z_first + it + 1) + pl;
-                      int       sl = slot0 + K + pl;
-                      sl -= (sl >= RING) ? RING : 0;
-                      sl -= (sl >= RING) ? RING : 0;
-                      const unsigned int sp = (unsigned int)__cvta_generic_to_shared(U + sl * PL + (pf_off[i] & 0xffff));
-                      const int          sz = ((pf_off[i] >> 30) || gz == n1 - 1) ? 0 : 8;
-                      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sp), "l"(pf_base + pf_goff[i]), "r"(sz));
+                      const bool last = (pf_s[i] >> 29) & 1;
+                      const int  so   = (last ? nn : nxt) + (pf_s[i] & 0xffffff);
+                      const unsigned int sp = (unsigned int)__cvta_generic_to_shared(U + so);
+                      const int          sz = ((pf_s[i] >> 30) || (last && top)) ? 0 : 8;
+                      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sp), "l"(pf_base + pf_g[i]), "r"(sz));
                     }
                 asm volatile("cp.async.commit_group;\n" ::);
                 pf_base += K * plane;
@@ -174,51 +190,61 @@ namespace spirk
             const int buf = it & 1;
             if (it >= 2)
               bar_sync(BAR_AB_EMPTY + buf, TA + TB); // group B has released this buffer
-#pragma unroll 1
-            for (int w = 0; w < IPT; ++w)
+            if (act)
               {
-                const int e = t + w * TA;
-                if (e < C::itemsA)
+#pragma unroll 1
+                for (int w = 0; w < 2; ++w)
                   {
-                    const int seg = e % TX, off = ((e / TX) % LY) * LX + K * seg, zl = e / (TX * LY);
-                    int       sl  = slot0 + zl;
-                    sl -= (sl >= RING) ? RING : 0;
-                    const double *row = U + sl * PL + off;
-                    double        u[n], av[n], bv[n];
+                    const int zl = 2 * pg + w;
+                    if (zl < n)
+                      {
+                        const double *row = U + (zl < K ? cur + zl * PLP : nxt) + off;
+                        double        u[n], av[n], bv[n];
 #pragma unroll
-                    for (int j = 0; j < n; ++j)
-                      u[j] = row[j];
-                    matvec<n>(Mh, u, av);
-                    matvec<n>(Kh, u, bv);
-                    if (seg > 0)
-                      { // finish the node shared with the previous cell of the tile: its row K
-                        double am = Mh[K * n + K] * u[0], ak = Kh[K * n + K] * u[0];
-#pragma unroll
-                        for (int j = 0; j < K; ++j)
+                        for (int j = 0; j < K; j += 2)
                           {
-                            const double up = row[j - K];
-                            am              = fma(Mh[K * n + j], up, am);
-                            ak              = fma(Kh[K * n + j], up, ak);
+                            const double2 v = *reinterpret_cast<const double2 *>(row + j);
+                            u[j] = v.x, u[j + 1] = v.y;
                           }
-                        av[0] += am, bv[0] += ak;
-                      }
-                    double *oa = AB + (buf * 2 * n + zl) * PL + off, *ob = oa + n * PL;
+                        u[K] = row[K];
+                        matvec<n>(Mh, u, av);
+                        matvec<n>(Kh, u, bv);
+                        if (seg > 0)
+                          { // finish the node shared with the previous cell of the tile: its row K
+                            double am = Mh[K * n + K] * u[0], ak = Kh[K * n + K] * u[0];
 #pragma unroll
-                    for (int i = 0; i < K; ++i)
-                      oa[i] = av[i], ob[i] = bv[i];
-                    if (seg == TX - 1)
-                      oa[K] = av[K], ob[K] = bv[K];
+                            for (int j = 0; j < K; j += 2)
+                              {
+                                const double2 v = *reinterpret_cast<const double2 *>(row + j - K);
+                                am = fma(Mh[K * n + j], v.x, am), ak = fma(Kh[K * n + j], v.x, ak);
+                                am = fma(Mh[K * n + j + 1], v.y, am), ak = fma(Kh[K * n + j + 1], v.y, ak);
+                              }
+                            av[0] += am, bv[0] += ak;
+                          }
+                        double *oa = AB + (buf * 2 * n + zl) * PLP + off, *ob = oa + n * PLP;
+#pragma unroll
+                        for (int i = 0; i < K; i += 2)
+                          {
+                            *reinterpret_cast<double2 *>(oa + i) = make_double2(av[i], av[i + 1]);
+                            *reinterpret_cast<double2 *>(ob + i) = make_double2(bv[i], bv[i + 1]);
+                          }
+                        if (seg == TX - 1)
+                          oa[K] = av[K], ob[K] = bv[K];
+                      }
                   }
               }
             bar_arrive(BAR_AB_FULL + buf, TA + TB);
-            slot0 += K;
-            slot0 -= (slot0 >= RING) ? RING : 0;
+            const int tmp = cur;
+            cur = nxt, nxt = nn, nn = tmp;
           }
       }
     else if (threadIdx.x < TA + TB)
       {
         // =========================== group B: y-lines ===========================
-        const int    t  = threadIdx.x - TA;
+        const int    t    = threadIdx.x - TA;
+        const int    pair = t % C::pairsB, pg = t / C::pairsB;
+        const int    seg  = pair / LX, off = (K * seg) * LXP + pair % LX;
+        const bool   act  = pg < NPG;
         const double cm = a.cm[b], cl = a.cl[b];
         for (int it = 0; it < n_layers; ++it)
           {
@@ -226,62 +252,65 @@ namespace spirk
             bar_sync(BAR_AB_FULL + buf, TA + TB);
             if (it >= 2)
               bar_sync(BAR_SP_EMPTY + buf, TB + TC);
-#pragma unroll 1
-            for (int w = 0; w < IPT; ++w)
+            if (act)
               {
-                const int e = t + w * TB;
-                if (e < C::itemsB)
+#pragma unroll 1
+                for (int w = 0; w < 2; ++w)
                   {
-                    const int     seg = (e / LX) % TY, off = (K * seg) * LX + e % LX, zl = e / (LX * TY);
-                    const double *ca = AB + (buf * 2 * n + zl) * PL + off, *cb = ca + n * PL;
-                    double        av[n], pv[n], q[n], sv[n];
-#pragma unroll
-                    for (int j = 0; j < n; ++j)
-                      av[j] = ca[j * LX];
-                    matvec<n>(Mh, av, pv);
-                    matvec<n>(Kh, av, q);
-                    if (seg > 0)
+                    const int zl = 2 * pg + w;
+                    if (zl < n)
                       {
-                        double pm = Mh[K * n + K] * av[0], qk = Kh[K * n + K] * av[0];
-#pragma unroll
-                        for (int j = 0; j < K; ++j)
-                          {
-                            const double ap = ca[(j - K) * LX];
-                            pm              = fma(Mh[K * n + j], ap, pm);
-                            qk              = fma(Kh[K * n + j], ap, qk);
-                          }
-                        pv[0] += pm, q[0] += qk;
-                      }
-                    // s = cm p + cl (q + My b): fold the b column into q with b pre-scaled by cl
-#pragma unroll
-                    for (int i = 0; i < n; ++i)
-                      q[i] = fma(cm, pv[i], cl * q[i]);
-#pragma unroll
-                    for (int j = 0; j < n; ++j)
-                      av[j] = cl * cb[j * LX];
-#pragma unroll
-                    for (int i = 0; i < n; ++i)
-                      {
-                        double acc = q[i];
+                        const double *ca = AB + (buf * 2 * n + zl) * PLP + off, *cb = ca + n * PLP;
+                        double        av[n], pv[n], q[n], sv[n];
 #pragma unroll
                         for (int j = 0; j < n; ++j)
-                          acc = fma(Mh[i * n + j], av[j], acc);
-                        sv[i] = acc;
-                      }
-                    if (seg > 0)
-                      {
-                        double rm = Mh[K * n + K] * av[0];
+                          av[j] = ca[j * LXP];
+                        matvec<n>(Mh, av, pv);
+                        matvec<n>(Kh, av, q);
+                        if (seg > 0)
+                          {
+                            double pm = Mh[K * n + K] * av[0], qk = Kh[K * n + K] * av[0];
 #pragma unroll
-                        for (int j = 0; j < K; ++j)
-                          rm = fma(Mh[K * n + j], cl * cb[(j - K) * LX], rm);
-                        sv[0] += rm;
-                      }
-                    double *os = SP + (buf * 2 * n + zl) * PL + off, *op = os + n * PL;
+                            for (int j = 0; j < K; ++j)
+                              {
+                                const double ap = ca[(j - K) * LXP];
+                                pm              = fma(Mh[K * n + j], ap, pm);
+                                qk              = fma(Kh[K * n + j], ap, qk);
+                              }
+                            pv[0] += pm, q[0] += qk;
+                          }
+                        // s = cm p + cl (q + My b): fold the b column into q with b pre-scaled by cl
 #pragma unroll
-                    for (int i = 0; i < K; ++i)
-                      os[i * LX] = sv[i], op[i * LX] = pv[i];
-                    if (seg == TY - 1)
-                      os[K * LX] = sv[K], op[K * LX] = pv[K];
+                        for (int i = 0; i < n; ++i)
+                          q[i] = fma(cm, pv[i], cl * q[i]);
+#pragma unroll
+                        for (int j = 0; j < n; ++j)
+                          av[j] = cl * cb[j * LXP];
+#pragma unroll
+                        for (int i = 0; i < n; ++i)
+                          {
+                            double acc = q[i];
+#pragma unroll
+                            for (int j = 0; j < n; ++j)
+                              acc = fma(Mh[i * n + j], av[j], acc);
+                            sv[i] = acc;
+                          }
+                        if (seg > 0)
+                          {
+                            double rm = Mh[K * n + K] * av[0];
+#pragma unroll
+                            for (int j = 0; j < K; ++j)
+                              rm = fma(Mh[K * n + j], cl * cb[(j - K) * LXP], rm);
+                            sv[0] += rm;
+                          }
+                        // group C only needs s and cl * p
+                        double *os = SP + (buf * 2 * n + zl) * PLP + off, *op = os + n * PLP;
+#pragma unroll
+                        for (int i = 0; i < K; ++i)
+                          os[i * LXP] = sv[i], op[i * LXP] = cl * pv[i];
+                        if (seg == TY - 1)
+                          os[K * LXP] = sv[K], op[K * LXP] = cl * pv[K];
+                      }
                   }
               }
             if (it + 2 < n_layers)
@@ -292,10 +321,12 @@ namespace spirk
     else if (threadIdx.x < TA + TB + TC)
       {
         // =========================== group C: z-lines ===========================
-        const int    t  = threadIdx.x - TA - TB;
-        const double cl = a.cl[b];
-        static_assert(IPT == 2, "group C keeps one carry register per item");
-        double carry0 = 0.0, carry1 = 0.0;
+        // one thread owns up to three node columns; the top plane of a layer is carried in registers
+        const int t  = threadIdx.x - TA - TB;
+        const int e0 = t, e1 = t + TC, e2 = t + 2 * TC;
+        const int o0 = (e0 / LX) * LXP + e0 % LX, o1 = (e1 / LX) * LXP + e1 % LX, o2 = (e2 / LX) * LXP + e2 % LX;
+        const int ncol = (e2 < LX * LY) ? 3 : (e1 < LX * LY) ? 2 : (e0 < LX * LY) ? 1 : 0;
+        double    carry0 = 0.0, carry1 = 0.0, carry2 = 0.0;
         for (int it = 0; it < n_layers; ++it)
           {
             const int buf = it & 1;
@@ -303,35 +334,34 @@ namespace spirk
             if (it >= 2)
               bar_sync(BAR_OUT_EMPTY + buf, TC + TD);
 #pragma unroll 1
-            for (int w = 0; w < IPT; ++w)
+            for (int w = 0; w < ncol; ++w)
               {
-                const int e = t + w * TC;
-                if (e < C::itemsC)
+                const int     o  = (w == 0) ? o0 : (w == 1) ? o1 : o2;
+                const double *cs = SP + (buf * 2 * n) * PLP + o, *cp = cs + n * PLP;
+                double        s[n], p[n], val[n];
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+                  s[z] = cs[z * PLP], p[z] = cp[z * PLP];
+#pragma unroll
+                for (int z = 0; z < n; ++z)
                   {
-                    const double *cs = SP + (buf * 2 * n) * PL + e, *cp = cs + n * PL;
-                    double        s[n], p[n], val[n];
+                    double acc = 0.0;
 #pragma unroll
-                    for (int z = 0; z < n; ++z)
-                      s[z] = cs[z * PL], p[z] = cl * cp[z * PL];
-#pragma unroll
-                    for (int z = 0; z < n; ++z)
-                      {
-                        double acc = 0.0;
-#pragma unroll
-                        for (int j = 0; j < n; ++j)
-                          acc = fma(Mh[z * n + j], s[j], fma(Kh[z * n + j], p[j], acc));
-                        val[z] = acc;
-                      }
-                    val[0] += (w == 0) ? carry0 : carry1;
-                    if (w == 0)
-                      carry0 = val[K];
-                    else
-                      carry1 = val[K];
-                    double *o = OUT + buf * K * PL + e;
-#pragma unroll
-                    for (int z = 0; z < K; ++z)
-                      o[z * PL] = val[z];
+                    for (int j = 0; j < n; ++j)
+                      acc = fma(Mh[z * n + j], s[j], fma(Kh[z * n + j], p[j], acc));
+                    val[z] = acc;
                   }
+                val[0] += (w == 0) ? carry0 : (w == 1) ? carry1 : carry2;
+                if (w == 0)
+                  carry0 = val[K];
+                else if (w == 1)
+                  carry1 = val[K];
+                else
+                  carry2 = val[K];
+                double *ov = OUT + buf * K * PLP + o;
+#pragma unroll
+                for (int z = 0; z < K; ++z)
+                  ov[z * PLP] = val[z];
               }
             if (it + 2 < n_layers)
               bar_arrive(BAR_SP_EMPTY + buf, TB + TC);
@@ -341,76 +371,137 @@ namespace spirk
     else
       {
         // =========================== group D: epilogue / stores ===========================
-        // streams the k finished node planes of a layer: interior nodes get the fused epilogue, wall
-        // nodes their slot (E + F * partial, E only from the carrier = low side in x and y)
-        const int    t  = threadIdx.x - TA - TB - TC;
-        const double f1 = a.f1[b], f2 = a.f2[b];
+        // streams the k finished node planes of a layer.  Interior nodes: fused epilogue E + F * Ax with
+        // plain coalesced stores.  Wall nodes: the slot value E + F * partial goes to the wall arrays
+        // (E only from the carrier = the contributor on the low side in x and y).  The epilogue operands
+        // (rhs, dinv, src, x_old) are staged one layer ahead with cp.async into thread-private shared
+        // slots, so their DRAM latency overlaps the previous layer.
+        const int     t  = threadIdx.x - TA - TB - TC;
+        const double  f1 = a.f1[b], f2 = a.f2[b];
+        constexpr int IX = LX - 2, IY = LY - 2, NINT = K * IX * IY, NI = (NINT + TD - 1) / TD;
+        constexpr int NW = 2 * LX + 2 * IY, NWALL = K * NW, NWI = (NWALL + TD - 1) / TD;
+        constexpr int NE = NI + NWI, NOPS = C::nops(MODE);
+        int           e_s[NE], e_g[NE]; // OUT-tile offset (-1: none; bit 30: plane z == 0), DoF offset in the layer
+        int           w_o[NWI], w_k[NWI]; // wall elements: slot offset, kind | carrier << 4
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+          {
+            const int q = t + i * TD;
+            const int z = q / (IX * IY), r = q % (IX * IY), cY = 1 + r / IX, cX = 1 + r % IX;
+            e_s[i] = (q < NINT) ? (z * PLP + cY * LXP + cX) | (z == 0 ? (1 << 30) : 0) : -1;
+            e_g[i] = (gx0 + cX) + n1 * (gy0 + cY) + (int)plane * z;
+          }
+#pragma unroll
+        for (int i = 0; i < NWI; ++i)
+          {
+            const int q = t + i * TD;
+            const int z = q / NW, r = q % NW;
+            int       cX, cY;
+            if (r < LX)
+              cX = r, cY = 0;
+            else if (r < 2 * LX)
+              cX = r - LX, cY = LY - 1;
+            else
+              cY = 1 + (r - 2 * LX) / 2, cX = ((r - 2 * LX) & 1) ? LX - 1 : 0;
+            const int  gx = gx0 + cX, gy = gy0 + cY;
+            const bool wallx = (cX == 0) || (cX == LX - 1), wally = (cY == 0) || (cY == LY - 1);
+            const int  wx = tx + (cX == 0 ? 0 : 1), dx = (cX == 0) ? 1 : 0;
+            const int  wy = ty + (cY == 0 ? 0 : 1), dy = (cY == 0) ? 1 : 0;
+            e_s[NI + i] = (q < NWALL) ? z * PLP + cY * LXP + cX : -1;
+            e_g[NI + i] = gx + n1 * gy + (int)plane * z;
+            if (wallx && wally)
+              w_o[i] = (((dy * 2 + dx) * (a.ntx + 1) + wx) * (a.nty + 1) + wy) * n1 + z, w_k[i] = 3 | ((dx == 0 && dy == 0) ? 16 : 0);
+            else if (wallx)
+              w_o[i] = (dx * (a.ntx + 1) + wx) * (int)plane + z * n1 + gy, w_k[i] = 1 | (dx == 0 ? 16 : 0);
+            else
+              w_o[i] = (dy * (a.nty + 1) + wy) * (int)plane + z * n1 + gx, w_k[i] = 2 | (dy == 0 ? 16 : 0);
+          }
+        const bool has_xo = a.x_old != nullptr;
+        // Operand pipeline: the operands of layer L+1 are loaded into registers while layer L is finished;
+        // E and F of the current layer wait in thread-private shared slots EF[E|F][element][thread].
+        double *EF = OUT + 2 * K * PLP + t;
+        double  pre[NOPS > 0 ? NOPS : 1][NE];
+        auto    load_ops = [&](const long long lay_) {
+#pragma unroll
+          for (int i = 0; i < NE; ++i)
+            if (e_s[i] >= 0)
+              {
+                const long long j = lay_ + e_g[i];
+                if (NOPS > 0)
+                  pre[0][i] = a.rhs[j];
+                if (NOPS > 1)
+                  {
+                    pre[1][i] = a.dinv[j];
+                    pre[2][i] = a.src[j];
+                    pre[3][i] = has_xo ? a.x_old[j] : 0.0;
+                  }
+              }
+        };
+        // running layer bases
+        long long lay = boff + plane * ((long long)K * z_first); // DoF index of plane 0 of the current layer
+        double   *wxb = a.WX + b * a.wx_block + (long long)(K * z_first) * n1;
+        double   *wyb = a.WY + b * a.wy_block + (long long)(K * z_first) * n1;
+        double   *wcb = a.WC + b * a.wc_block + (K * z_first);
+        load_ops(lay);
         for (int it = 0; it < n_layers; ++it)
           {
-            const int  buf = it & 1, zc = z_first + it;
+            const int buf = it & 1, zc = z_first + it;
+            // E + F * Ax for this layer's elements (E only from the carrier on walls)
+            if (NOPS > 0)
+              {
+#pragma unroll
+                for (int i = 0; i < NE; ++i)
+                  if (e_s[i] >= 0)
+                    {
+                      const bool carrier = (i >= NI) ? (w_k[i >= NI ? i - NI : 0] & 16) : true;
+                      double     F = -1.0, E = carrier ? pre[0][i] : 0.0;
+                      if (MODE == V2_CHEB)
+                        {
+                          F = -f2 * pre[1][i];
+                          E = carrier ? (1.0 + f1) * pre[2][i] - f1 * pre[3][i] - F * pre[0][i] : 0.0;
+                        }
+                      EF[i * TD] = E, EF[(NE + i) * TD] = F;
+                    }
+                if (it + 1 < n_layers)
+                  load_ops(lay + K * plane); // in flight while this layer is finished
+              }
             bar_sync(BAR_OUT_FULL + buf, TC + TD);
             if (zc >= zb)
               {
-#pragma unroll 2
-                for (int e = t; e < K * PL; e += TD)
-                  {
-                    const int       cX = e % LX, cY = (e / LX) % LY, z = e / PL;
-                    const double    v  = OUT[buf * K * PL + e];
-                    const int       gx = gx0 + cX, gy = gy0 + cY, gz = K * zc + z;
-                    const long long j  = boff + gx + (long long)n1 * gy + plane * gz;
-                    const bool      wallx = (cX == 0) || (cX == LX - 1), wally = (cY == 0) || (cY == LY - 1);
-                    const bool      is_wall = wallx || wally;
-                    double         *out     = a.dst + j;
-                    bool            carrier = true;
-                    if (is_wall)
-                      {
-                        const int wx = tx + (cX == 0 ? 0 : 1), dx = (cX == 0) ? 1 : 0;
-                        const int wy = ty + (cY == 0 ? 0 : 1), dy = (cY == 0) ? 1 : 0;
-                        if (wallx && wally)
-                          out = a.WC + b * a.wc_block + (((long long)(dy * 2 + dx) * (a.ntx + 1) + wx) * (a.nty + 1) + wy) * n1 + gz,
-                          carrier = (dx == 0 && dy == 0);
-                        else if (wallx)
-                          out = a.WX + b * a.wx_block + ((long long)dx * (a.ntx + 1) + wx) * plane + (long long)gz * n1 + gy,
-                          carrier = (dx == 0);
-                        else
-                          out = a.WY + b * a.wy_block + ((long long)dy * (a.nty + 1) + wy) * plane + (long long)gz * n1 + gx,
-                          carrier = (dy == 0);
-                      }
-                    double E = 0.0, F = 1.0;
-                    if (MODE == V2_RESIDUAL)
-                      {
-                        F = -1.0;
-                        E = carrier ? a.rhs[j] : 0.0;
-                      }
-                    else if (MODE == V2_CHEB)
-                      {
-                        F = -f2 * a.dinv[j];
-                        if (carrier)
-                          {
-                            const double xo = a.x_old ? a.x_old[j] : 0.0;
-                            E               = (1.0 + f1) * a.src[j] - f1 * xo - F * a.rhs[j];
-                          }
-                      }
-                    double Ax = v;
-                    if (!is_wall && gz == 0) // Dirichlet plane gz = 0: A is the identity there
-                      Ax = a.src[j];
-                    *out = fma(F, Ax, E);
-                  }
+                const double *tile = OUT + buf * K * PLP;
+#pragma unroll
+                for (int i = 0; i < NE; ++i)
+                  if (e_s[i] >= 0)
+                    {
+                      const long long j = lay + e_g[i];
+                      double          v = tile[e_s[i] & 0xffffff], F = 1.0, E = 0.0;
+                      if (NOPS > 0)
+                        E = EF[i * TD], F = EF[(NE + i) * TD];
+                      if (i < NI)
+                        {
+                          if (zc == 0 && (e_s[i] >> 30)) // Dirichlet plane gz = 0: A is the identity there
+                            v = a.src[j];
+                          a.dst[j] = fma(F, v, E);
+                        }
+                      else
+                        {
+                          const int kind = w_k[i >= NI ? i - NI : 0] & 3;
+                          double   *slot = (kind == 1 ? wxb : kind == 2 ? wyb : wcb) + w_o[i >= NI ? i - NI : 0];
+                          *slot          = fma(F, v, E);
+                        }
+                    }
               }
             if (it + 2 < n_layers)
               bar_arrive(BAR_OUT_EMPTY + buf, TC + TD);
+            lay += K * plane, wxb += K * n1, wyb += K * n1, wcb += K;
           }
         // top plane of the domain (Dirichlet): interior node columns of the last chunk
         if (ze == nc)
-          for (int e = t; e < PL; e += TD)
+          for (int r = t; r < IX * IY; r += TD)
             {
-              const int cX = e % LX, cY = e / LX;
-              if (cX > 0 && cX < LX - 1 && cY > 0 && cY < LY - 1)
-                {
-                  const long long gi = (gx0 + cX) + (long long)n1 * (gy0 + cY) + plane * (n1 - 1);
-                  const double    x  = src[gi];
-                  v2_epilogue(a, b, boff + gi, x, x);
-                }
+              const long long gi = (gx0 + 1 + r % IX) + (long long)n1 * (gy0 + 1 + r / IX) + plane * (n1 - 1);
+              const double    x  = src[gi];
+              v2_epilogue(a, b, boff + gi, x, x);
             }
       }
   }
@@ -491,9 +582,9 @@ namespace spirk
     static bool attr_set = false;
     if (!attr_set)
       {
-        SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
-        SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
-        SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(V2_APPLY)));
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(V2_RESIDUAL)));
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(V2_CHEB)));
         attr_set = true;
       }
     const int n1 = a.g.n1;
@@ -533,11 +624,11 @@ namespace spirk
     a.WC = a.WY + a.wy_block * a.nb;
     const long long grid = columns * a.nchunks * a.nb;
     if (a.mode == V2_APPLY)
-      k_v2_main<K, TX, TY, V2_APPLY><<<(unsigned int)grid, C::threads, C::smem, ctx->stream>>>(a);
+      k_v2_main<K, TX, TY, V2_APPLY><<<(unsigned int)grid, C::threads, C::smem(V2_APPLY), ctx->stream>>>(a);
     else if (a.mode == V2_RESIDUAL)
-      k_v2_main<K, TX, TY, V2_RESIDUAL><<<(unsigned int)grid, C::threads, C::smem, ctx->stream>>>(a);
+      k_v2_main<K, TX, TY, V2_RESIDUAL><<<(unsigned int)grid, C::threads, C::smem(V2_RESIDUAL), ctx->stream>>>(a);
     else
-      k_v2_main<K, TX, TY, V2_CHEB><<<(unsigned int)grid, C::threads, C::smem, ctx->stream>>>(a);
+      k_v2_main<K, TX, TY, V2_CHEB><<<(unsigned int)grid, C::threads, C::smem(V2_CHEB), ctx->stream>>>(a);
     SPIRK_LAUNCH_CHECK(ctx);
     const int  per_plane = (a.ntx + 1) * n1 + (a.nty + 1) * n1 + (a.ntx + 1) * (a.nty + 1);
     const dim3 wgrid((per_plane + 255) / 256, n1, a.nb);
@@ -552,7 +643,7 @@ namespace spirk
                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
                       const double *f2)
   {
-    if (g.dim != 3 || g.k != 4 || op->kind != SPIRK_OP_REAL || g.nc % 4 != 0 || g.nc < 8)
+    if (g.dim != 3 || g.k != 4 || op->kind != SPIRK_OP_REAL || g.nc % 8 != 0 || g.nc < 8)
       return SPIRK_ERR_UNSUPPORTED;
     V2Args a;
     a.g = g, a.mode = mode, a.nb = op->nb, a.stride = stride;
@@ -563,6 +654,8 @@ namespace spirk
         a.cm[b] = op->mass[b] * hd, a.cl[b] = op->laplace[b] * hl;
         a.f1[b] = f1 ? f1[b] : 0.0, a.f2[b] = f2 ? f2[b] : 0.0;
       }
-    return v2_launch<4, 4, 4>(ctx, a);
+    if (ctx->opt_apply_variant == 3)
+      return v2_launch<4, 4, 4>(ctx, a);
+    return v2_launch<4, 8, 2>(ctx, a);
   }
 } // namespace spirk
