@@ -426,8 +426,25 @@ struct spirk_ctx
 };
 struct spirk_comm
 {
-  int dummy;
+  int rank, n_ranks;
 };
+// TEST-ONLY multi-rank hook: the CPU double has no transport of its own; a test process may register
+// callbacks (e.g. torch.distributed / gloo from Python) that carry the collectives, so that the
+// stage-parallel host logic can be exercised with world_size > 1 on CPU.
+typedef void (*spirk_cpu_allreduce_fn)(double *buf, long long n);
+typedef void (*spirk_cpu_allgather_fn)(double *recv, const double *send, long long n);
+namespace
+{
+  int                    g_cpu_rank = 0, g_cpu_size = 1;
+  spirk_cpu_allreduce_fn g_cpu_allreduce = nullptr;
+  spirk_cpu_allgather_fn g_cpu_allgather = nullptr;
+  thread_local spirk_comm *g_reduction_comm = nullptr;
+  inline void reduce_scalar(double *r)
+  {
+    if (g_reduction_comm && g_reduction_comm->n_ranks > 1 && g_cpu_allreduce)
+      g_cpu_allreduce(r, 1);
+  }
+} // namespace
 
 extern "C" {
 
@@ -786,6 +803,7 @@ int spirk_vec_dot(spirk_ctx *, const double *x, const double *y, long long n, do
   for (long long i = 0; i < n; ++i)
     s += x[i] * y[i];
   *r = s;
+  reduce_scalar(r);
   return SPIRK_OK;
 }
 int spirk_vec_add_and_dot(spirk_ctx *, double *v, double a, const double *V, const double *W, long long n, double *r)
@@ -798,6 +816,7 @@ int spirk_vec_add_and_dot(spirk_ctx *, double *v, double a, const double *V, con
       s += v[i] * W[i];
     }
   *r = s;
+  reduce_scalar(r);
   return SPIRK_OK;
 }
 int spirk_vec_sum(spirk_ctx *, const double *x, long long n, double *r)
@@ -975,17 +994,23 @@ int spirk_constraints_set_zero(spirk_ctx *, const spirk_level *lvl, int nb, doub
   return SPIRK_OK;
 }
 
-// ---------------------------------------------------------------- communication: single rank only
+// ---------------------------------------------------------------- communication: single rank, or
+// test-registered callbacks (see spirk_cpu_set_comm above)
+int spirk_cpu_set_comm(int rank, int size, spirk_cpu_allreduce_fn allreduce, spirk_cpu_allgather_fn allgather)
+{
+  g_cpu_rank = rank, g_cpu_size = size, g_cpu_allreduce = allreduce, g_cpu_allgather = allgather;
+  return SPIRK_OK;
+}
 int spirk_comm_unique_id(char *id)
 {
   std::memset(id, 0, 128);
   return SPIRK_OK;
 }
-int spirk_comm_create(spirk_ctx *, const char *, int n_ranks, int, spirk_comm **comm)
+int spirk_comm_create(spirk_ctx *, const char *, int n_ranks, int rank, spirk_comm **comm)
 {
-  if (n_ranks != 1)
-    return fail(SPIRK_ERR_UNSUPPORTED, "cpu oracle is single-rank");
-  *comm = new spirk_comm{0};
+  if (n_ranks != 1 && !(g_cpu_allreduce && g_cpu_allgather && n_ranks == g_cpu_size && rank == g_cpu_rank))
+    return fail(SPIRK_ERR_UNSUPPORTED, "cpu oracle: multi-rank needs spirk_cpu_set_comm callbacks");
+  *comm = new spirk_comm{rank, n_ranks};
   return SPIRK_OK;
 }
 int spirk_comm_destroy(spirk_comm *c)
@@ -993,17 +1018,28 @@ int spirk_comm_destroy(spirk_comm *c)
   delete c;
   return SPIRK_OK;
 }
-int spirk_comm_rank(const spirk_comm *, int *rank, int *n)
+int spirk_comm_rank(const spirk_comm *c, int *rank, int *n)
 {
-  *rank = 0, *n = 1;
+  *rank = c->rank, *n = c->n_ranks;
   return SPIRK_OK;
 }
-int spirk_comm_allreduce_sum(spirk_ctx *, spirk_comm *, double *, long long) { return SPIRK_OK; }
-int spirk_comm_allgather(spirk_ctx *, spirk_comm *, double *recv, const double *send, long long n)
+int spirk_comm_allreduce_sum(spirk_ctx *, spirk_comm *c, double *buf, long long n)
 {
-  if (recv != send)
+  if (c->n_ranks > 1)
+    g_cpu_allreduce(buf, n);
+  return SPIRK_OK;
+}
+int spirk_comm_allgather(spirk_ctx *, spirk_comm *c, double *recv, const double *send, long long n)
+{
+  if (c->n_ranks > 1)
+    g_cpu_allgather(recv, send, n);
+  else if (recv != send)
     std::memcpy(recv, send, n * sizeof(double));
   return SPIRK_OK;
 }
-int spirk_ctx_set_reduction_comm(spirk_ctx *, spirk_comm *) { return SPIRK_OK; }
+int spirk_ctx_set_reduction_comm(spirk_ctx *, spirk_comm *c)
+{
+  g_reduction_comm = c;
+  return SPIRK_OK;
+}
 }
