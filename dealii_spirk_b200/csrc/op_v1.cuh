@@ -328,7 +328,7 @@ namespace spirk
   __global__ void k_cheb_epilogue(const long long N, const int nb, double *x_new, const double *__restrict__ x,
                                   const double *x_old, const double *__restrict__ rhs, const double *__restrict__ dinv,
                                   const double *__restrict__ t, const long long stride, const long long tstride,
-                                  const ChebFactors f)
+                                  const ChebFactors f, const long long dstride)
   {
     const long long total = N * nb;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x)
@@ -336,7 +336,7 @@ namespace spirk
         const int       b  = e / N;
         const long long i  = e - b * N, j = b * stride + i;
         const double    xo = x_old ? x_old[j] : 0.0;
-        x_new[j]           = (1.0 + f.f1[b]) * x[j] - f.f1[b] * xo + f.f2[b] * dinv[j] * (rhs[j] - t[b * tstride + i]);
+        x_new[j]           = (1.0 + f.f1[b]) * x[j] - f.f1[b] * xo + f.f2[b] * dinv[b * dstride + i] * (rhs[j] - t[b * tstride + i]);
       }
   }
 

@@ -41,7 +41,8 @@ namespace spirk
   {
     V2_APPLY    = 0, // dst = A src
     V2_RESIDUAL = 1, // dst = rhs - A src
-    V2_CHEB     = 2  // dst = src + f1 (src - x_old) + f2 dinv (rhs - A src)
+    V2_CHEB     = 2, // dst = src + f1 (src - x_old) + f2 dinv (rhs - A src)
+    V2_CHEB_OWN = 3  // the same with dinv = the operator's own inverse diagonal, computed on the fly
   };
 
   template <int K, int TX, int TY>
@@ -57,13 +58,13 @@ namespace spirk
     static constexpr int TD = 320;                                 // epilogue / store warps
     static constexpr int threads = TA + TB + TC + TD;
     static constexpr int ringp   = 3 * K; // node-plane ring: 3 layers x K planes
-    // epilogue operands staged per layer: none (apply), rhs (residual), rhs + dinv + src + x_old (Chebyshev)
-    __host__ __device__ static constexpr int nops(const int mode) { return mode == 2 ? 4 : (mode == 1 ? 1 : 0); }
+    // operands staged with cp.async by the epilogue group: none (apply), rhs (residual), rhs + x_old (Chebyshev)
+    __host__ __device__ static constexpr int nops_async(const int mode) { return mode >= 2 ? 2 : (mode == 1 ? 1 : 0); }
     static constexpr int NE_D = (K * (LX - 2) * (LY - 2) + TD - 1) / TD + (K * (2 * LX + 2 * (LY - 2)) + TD - 1) / TD;
-    // ring + 2 x (A,B) + 2 x (S,P) + 2 x OUT + thread-private (E, F) slots of the epilogue group
+    // ring + 2 x (A,B) + 2 x (S,P) + 2 x OUT + 3-deep ring of thread-private operand slots of the epilogue group
     static constexpr size_t smem(const int mode)
     {
-      return sizeof(double) * ((size_t)(ringp + 8 * n + 2 * K) * PLP + (nops(mode) > 0 ? 2 * (size_t)NE_D * TD : 0));
+      return sizeof(double) * ((size_t)(ringp + 8 * n + 2 * K) * PLP + 3 * (size_t)nops_async(mode) * NE_D * TD);
     }
     static_assert(threads <= 1024, "tile too large for one CTA");
     static_assert(K % 2 == 0, "128-bit shared accesses need an even degree");
@@ -101,7 +102,9 @@ namespace spirk
     else
       {
         const double xo = a.x_old ? a.x_old[j] : 0.0;
-        a.dst[j]        = (1.0 + a.f1[b]) * x - a.f1[b] * xo + a.f2[b] * a.dinv[j] * (a.rhs[j] - Ax);
+        // dinv == NULL: only used for Dirichlet nodes when dinv == NULL (the inverse diagonal is 1 there)
+        const double di = a.dinv ? a.dinv[j] : 1.0;
+        a.dst[j]        = (1.0 + a.f1[b]) * x - a.f1[b] * xo + a.f2[b] * di * (a.rhs[j] - Ax);
       }
   }
 
@@ -372,24 +375,40 @@ namespace spirk
       {
         // =========================== group D: epilogue / stores ===========================
         // streams the k finished node planes of a layer.  Interior nodes: fused epilogue E + F * Ax with
-        // plain coalesced stores.  Wall nodes: the slot value E + F * partial goes to the wall arrays
-        // (E only from the carrier = the contributor on the low side in x and y).  The epilogue operands
-        // (rhs, dinv, src, x_old) are staged one layer ahead with cp.async into thread-private shared
-        // slots, so their DRAM latency overlaps the previous layer.
+        // plain stores.  Wall nodes: the slot value E + F * partial goes to the wall arrays (E only from
+        // the carrier = the contributor on the low side in x and y).  Operand pipeline: rhs (and x_old)
+        // are staged TWO layers ahead with cp.async into thread-private shared slots, x one layer ahead
+        // in registers (an L2 hit: group A has just streamed it), D^-1 is either loaded one layer ahead
+        // or - when the caller passes dinv == NULL - the operator's own inverse diagonal, which is the
+        // same for every layer of the sweep and computed once per element.
         const int     t  = threadIdx.x - TA - TB - TC;
         const double  f1 = a.f1[b], f2 = a.f2[b];
         constexpr int IX = LX - 2, IY = LY - 2, NINT = K * IX * IY, NI = (NINT + TD - 1) / TD;
         constexpr int NW = 2 * LX + 2 * IY, NWALL = K * NW, NWI = (NWALL + TD - 1) / TD;
-        constexpr int NE = NI + NWI, NOPS = C::nops(MODE);
+        constexpr int NE = NI + NWI, NAS = C::nops_async(MODE);
+        double       *OPS = OUT + 2 * K * PLP + t; // [ring of 3][operand][element][thread]
         int           e_s[NE], e_g[NE]; // OUT-tile offset (-1: none; bit 30: plane z == 0), DoF offset in the layer
         int           w_o[NWI], w_k[NWI]; // wall elements: slot offset, kind | carrier << 4
+        constexpr bool CHEB = (MODE == V2_CHEB || MODE == V2_CHEB_OWN), own_dinv = (MODE == V2_CHEB_OWN);
+        double        dloc[own_dinv ? NE : 1]; // on-the-fly inverse diagonal (dinv == NULL)
+        const double *Mh_ = Mh, *Kh_ = Kh;
+        auto diag_of = [&](const int cX, const int cY, const int z) {
+          // assembled 1-D diagonals at tile-local node (cX, cY) and plane z of a layer (not on the domain boundary)
+          const int    lx = cX % K, ly = cY % K;
+          const double mx = lx ? Mh_[lx * n + lx] : Mh_[0] + Mh_[K * n + K], kx = lx ? Kh_[lx * n + lx] : Kh_[0] + Kh_[K * n + K];
+          const double my = ly ? Mh_[ly * n + ly] : Mh_[0] + Mh_[K * n + K], ky = ly ? Kh_[ly * n + ly] : Kh_[0] + Kh_[K * n + K];
+          const double mz = z ? Mh_[z * n + z] : Mh_[0] + Mh_[K * n + K], kz = z ? Kh_[z * n + z] : Kh_[0] + Kh_[K * n + K];
+          const double d  = a.cm[b] * mx * my * mz + a.cl[b] * (kx * my * mz + mx * ky * mz + mx * my * kz);
+          return (fabs(d) > 1.0e-10) ? 1.0 / d : 1.0;
+        };
 #pragma unroll
         for (int i = 0; i < NI; ++i)
           {
             const int q = t + i * TD;
             const int z = q / (IX * IY), r = q % (IX * IY), cY = 1 + r / IX, cX = 1 + r % IX;
-            e_s[i] = (q < NINT) ? (z * PLP + cY * LXP + cX) | (z == 0 ? (1 << 30) : 0) : -1;
-            e_g[i] = (gx0 + cX) + n1 * (gy0 + cY) + (int)plane * z;
+            e_s[i]  = (q < NINT) ? (z * PLP + cY * LXP + cX) | (z == 0 ? (1 << 30) : 0) : -1;
+            e_g[i]  = (gx0 + cX) + n1 * (gy0 + cY) + (int)plane * z;
+            dloc[i] = (own_dinv) ? diag_of(cX, cY, z % K) : 0.0;
           }
 #pragma unroll
         for (int i = 0; i < NWI; ++i)
@@ -407,8 +426,9 @@ namespace spirk
             const bool wallx = (cX == 0) || (cX == LX - 1), wally = (cY == 0) || (cY == LY - 1);
             const int  wx = tx + (cX == 0 ? 0 : 1), dx = (cX == 0) ? 1 : 0;
             const int  wy = ty + (cY == 0 ? 0 : 1), dy = (cY == 0) ? 1 : 0;
-            e_s[NI + i] = (q < NWALL) ? z * PLP + cY * LXP + cX : -1;
-            e_g[NI + i] = gx + n1 * gy + (int)plane * z;
+            e_s[NI + i]  = (q < NWALL) ? z * PLP + cY * LXP + cX : -1;
+            e_g[NI + i]  = gx + n1 * gy + (int)plane * z;
+            dloc[NI + i] = (own_dinv) ? diag_of(cX, cY, z % K) : 0.0;
             if (wallx && wally)
               w_o[i] = (((dy * 2 + dx) * (a.ntx + 1) + wx) * (a.nty + 1) + wy) * n1 + z, w_k[i] = 3 | ((dx == 0 && dy == 0) ? 16 : 0);
             else if (wallx)
@@ -417,53 +437,79 @@ namespace spirk
               w_o[i] = (dy * (a.nty + 1) + wy) * (int)plane + z * n1 + gx, w_k[i] = 2 | (dy == 0 ? 16 : 0);
           }
         const bool has_xo = a.x_old != nullptr;
-        // Operand pipeline: the operands of layer L+1 are loaded into registers while layer L is finished;
-        // E and F of the current layer wait in thread-private shared slots EF[E|F][element][thread].
-        double *EF = OUT + 2 * K * PLP + t;
-        double  pre[NOPS > 0 ? NOPS : 1][NE];
-        auto    load_ops = [&](const long long lay_) {
+        // cp.async staging of rhs (and x_old) of the layer with plane-0 DoF index lay_ into ring slot sb_
+        auto stage = [&](const int sb_, const long long lay_, const bool valid) {
+          if (NAS > 0 && valid)
+            {
 #pragma unroll
-          for (int i = 0; i < NE; ++i)
-            if (e_s[i] >= 0)
-              {
-                const long long j = lay_ + e_g[i];
-                if (NOPS > 0)
-                  pre[0][i] = a.rhs[j];
-                if (NOPS > 1)
+              for (int i = 0; i < NE; ++i)
+                if (e_s[i] >= 0)
                   {
-                    pre[1][i] = a.dinv[j];
-                    pre[2][i] = a.src[j];
-                    pre[3][i] = has_xo ? a.x_old[j] : 0.0;
+                    const long long    j  = lay_ + e_g[i];
+                    const unsigned int sp = (unsigned int)__cvta_generic_to_shared(OPS + ((sb_ * NAS) * NE + i) * TD);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sp), "l"(a.rhs + j));
+                    if (NAS > 1 && has_xo)
+                      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sp + NE * TD * 8), "l"(a.x_old + j));
                   }
-              }
+            }
+          asm volatile("cp.async.commit_group;\n" ::);
+        };
+        double xc[NE], xn[NE], dn[own_dinv ? 1 : NE]; // x of the current / next layer, explicit dinv of the next layer
+        auto   load_x = [&](const long long lay_, double (&xv)[NE], double (&dv)[own_dinv ? 1 : NE]) {
+          if (CHEB)
+            {
+#pragma unroll
+              for (int i = 0; i < NE; ++i)
+                if (e_s[i] >= 0)
+                  {
+                    xv[i] = a.src[lay_ + e_g[i]];
+                    if (!own_dinv)
+                      dv[own_dinv ? 0 : i] = a.dinv[lay_ + e_g[i]];
+                  }
+            }
         };
         // running layer bases
         long long lay = boff + plane * ((long long)K * z_first); // DoF index of plane 0 of the current layer
         double   *wxb = a.WX + b * a.wx_block + (long long)(K * z_first) * n1;
         double   *wyb = a.WY + b * a.wy_block + (long long)(K * z_first) * n1;
         double   *wcb = a.WC + b * a.wc_block + (K * z_first);
-        load_ops(lay);
+        stage(0, lay, true);
+        stage(1, lay + K * plane, n_layers > 1);
+        double dc[own_dinv ? 1 : NE];
+        load_x(lay, xc, dc);
+        int sb = 0;
         for (int it = 0; it < n_layers; ++it)
           {
             const int buf = it & 1, zc = z_first + it;
+            int       sb2 = sb + 2;
+            sb2 -= (sb2 >= 3) ? 3 : 0;
+            stage(sb2, lay + 2 * K * plane, it + 2 < n_layers);
+            if (it + 1 < n_layers)
+              load_x(lay + K * plane, xn, dn);
+            asm volatile("cp.async.wait_group 2;\n" ::);
             // E + F * Ax for this layer's elements (E only from the carrier on walls)
-            if (NOPS > 0)
-              {
+            double E[NE], F[NE];
+            const double *ops = OPS + (sb * NAS) * NE * TD;
 #pragma unroll
-                for (int i = 0; i < NE; ++i)
-                  if (e_s[i] >= 0)
-                    {
-                      const bool carrier = (i >= NI) ? (w_k[i >= NI ? i - NI : 0] & 16) : true;
-                      double     F = -1.0, E = carrier ? pre[0][i] : 0.0;
-                      if (MODE == V2_CHEB)
-                        {
-                          F = -f2 * pre[1][i];
-                          E = carrier ? (1.0 + f1) * pre[2][i] - f1 * pre[3][i] - F * pre[0][i] : 0.0;
-                        }
-                      EF[i * TD] = E, EF[(NE + i) * TD] = F;
-                    }
-                if (it + 1 < n_layers)
-                  load_ops(lay + K * plane); // in flight while this layer is finished
+            for (int i = 0; i < NE; ++i)
+              {
+                E[i] = 0.0, F[i] = 1.0;
+                if (e_s[i] >= 0 && MODE != V2_APPLY)
+                  {
+                    const bool   carrier = (i >= NI) ? (w_k[i >= NI ? i - NI : 0] & 16) : true;
+                    const double rh      = ops[i * TD];
+                    if (MODE == V2_RESIDUAL)
+                      F[i] = -1.0, E[i] = carrier ? rh : 0.0;
+                    else
+                      {
+                        double di = own_dinv ? dloc[own_dinv ? i : 0] : dc[own_dinv ? 0 : i];
+                        if (zc == 0 && (e_s[i] >> 30) && i < NI)
+                          di = 1.0; // Dirichlet plane gz = 0
+                        const double xo = has_xo ? ops[(NE + i) * TD] : 0.0;
+                        F[i]            = -f2 * di;
+                        E[i]            = carrier ? (1.0 + f1) * xc[i] - f1 * xo - F[i] * rh : 0.0;
+                      }
+                  }
               }
             bar_sync(BAR_OUT_FULL + buf, TC + TD);
             if (zc >= zb)
@@ -474,26 +520,32 @@ namespace spirk
                   if (e_s[i] >= 0)
                     {
                       const long long j = lay + e_g[i];
-                      double          v = tile[e_s[i] & 0xffffff], F = 1.0, E = 0.0;
-                      if (NOPS > 0)
-                        E = EF[i * TD], F = EF[(NE + i) * TD];
+                      double          v = tile[e_s[i] & 0xffffff];
                       if (i < NI)
                         {
                           if (zc == 0 && (e_s[i] >> 30)) // Dirichlet plane gz = 0: A is the identity there
-                            v = a.src[j];
-                          a.dst[j] = fma(F, v, E);
+                            v = CHEB ? xc[i] : a.src[j];
+                          a.dst[j] = fma(F[i], v, E[i]);
                         }
                       else
                         {
                           const int kind = w_k[i >= NI ? i - NI : 0] & 3;
                           double   *slot = (kind == 1 ? wxb : kind == 2 ? wyb : wcb) + w_o[i >= NI ? i - NI : 0];
-                          *slot          = fma(F, v, E);
+                          *slot          = fma(F[i], v, E[i]);
                         }
                     }
               }
             if (it + 2 < n_layers)
               bar_arrive(BAR_OUT_EMPTY + buf, TC + TD);
             lay += K * plane, wxb += K * n1, wyb += K * n1, wcb += K;
+            sb = (sb == 2) ? 0 : sb + 1;
+#pragma unroll
+            for (int i = 0; i < NE; ++i)
+              {
+                xc[i] = xn[i];
+                if (!own_dinv)
+                  dc[own_dinv ? 0 : i] = dn[own_dinv ? 0 : i];
+              }
           }
         // top plane of the domain (Dirichlet): interior node columns of the last chunk
         if (ze == nc)
@@ -585,6 +637,7 @@ namespace spirk
         SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(V2_APPLY)));
         SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(V2_RESIDUAL)));
         SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_CHEB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(V2_CHEB)));
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v2_main<K, TX, TY, V2_CHEB_OWN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem(V2_CHEB_OWN)));
         attr_set = true;
       }
     const int n1 = a.g.n1;
@@ -627,8 +680,10 @@ namespace spirk
       k_v2_main<K, TX, TY, V2_APPLY><<<(unsigned int)grid, C::threads, C::smem(V2_APPLY), ctx->stream>>>(a);
     else if (a.mode == V2_RESIDUAL)
       k_v2_main<K, TX, TY, V2_RESIDUAL><<<(unsigned int)grid, C::threads, C::smem(V2_RESIDUAL), ctx->stream>>>(a);
-    else
+    else if (a.dinv != nullptr)
       k_v2_main<K, TX, TY, V2_CHEB><<<(unsigned int)grid, C::threads, C::smem(V2_CHEB), ctx->stream>>>(a);
+    else
+      k_v2_main<K, TX, TY, V2_CHEB_OWN><<<(unsigned int)grid, C::threads, C::smem(V2_CHEB_OWN), ctx->stream>>>(a);
     SPIRK_LAUNCH_CHECK(ctx);
     const int  per_plane = (a.ntx + 1) * n1 + (a.nty + 1) * n1 + (a.ntx + 1) * (a.nty + 1);
     const dim3 wgrid((per_plane + 255) / 256, n1, a.nb);

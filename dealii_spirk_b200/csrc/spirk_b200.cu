@@ -452,15 +452,28 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
       if (st != SPIRK_ERR_UNSUPPORTED)
         return st;
     }
-  if (int e = ensure_scratch(ctx, (size_t)g.N * op->nb))
+  // general path: A x into scratch, then the pointwise update; dinv == NULL -> the operator's own
+  // inverse diagonal (REAL operators only), materialised behind A x in the scratch buffer
+  const bool own_dinv = (dinv == nullptr);
+  if (own_dinv && op->kind != SPIRK_OP_REAL)
+    return set_error(SPIRK_ERR_INVALID, "op_cheb_step: dinv == NULL needs a REAL operator");
+  if (int e = ensure_scratch(ctx, (size_t)g.N * op->nb * (own_dinv ? 2 : 1)))
     return e;
+  if (own_dinv)
+    {
+      double *d = ctx->d_scratch + (size_t)g.N * op->nb;
+      for (int b = 0; b < op->nb; ++b)
+        if (int e = spirk_op_inverse_diagonal(ctx, lvl, d + (size_t)b * g.N, op->mass[b], op->laplace[b]))
+          return e;
+    }
   if (int e = apply_any(ctx, g, op, ctx->d_scratch, x, g.N))
     return e;
   ChebFactors f;
   for (int b = 0; b < op->nb; ++b)
     f.f1[b] = f1[b], f.f2[b] = f2[b];
-  k_cheb_epilogue<<<grid_for(ctx, g.N * op->nb, 256), 256, 0, ctx->stream>>>(g.N, op->nb, x_new, x, x_old, rhs, dinv, ctx->d_scratch,
-                                                                              stride, g.N, f);
+  k_cheb_epilogue<<<grid_for(ctx, g.N * op->nb, 256), 256, 0, ctx->stream>>>(
+    g.N, op->nb, x_new, x, x_old, rhs, own_dinv ? ctx->d_scratch + (size_t)g.N * op->nb : dinv, ctx->d_scratch, stride, g.N, f,
+    own_dinv ? g.N : stride);
   SPIRK_LAUNCH_CHECK(ctx);
   return SPIRK_OK;
 }

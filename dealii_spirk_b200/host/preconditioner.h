@@ -142,6 +142,9 @@ namespace spirk_host
       Vector              dinv;
       std::vector<double> theta, delta; // per block
       std::vector<double> max_eigenvalue, min_eigenvalue;
+      // coefficients (mass, laplace) the inverse diagonal of block b was computed with; when they
+      // equal the live operator's, the smoother lets the kernel form D^-1 on the fly (dinv == NULL)
+      std::vector<double> dinv_mass, dinv_laplace;
       unsigned int        cg_iterations = 0;
       Vector              defect, solution, t, d, tmp;
     };
@@ -192,6 +195,9 @@ namespace spirk_host
           }
         if (!any)
           return;
+        bool own_dinv = op.kind == SPIRK_OP_REAL && (int)L.dinv_mass.size() == nb;
+        for (int i = 0; own_dinv && i < nb; ++i)
+          own_dinv = L.dinv_mass[i] == op.mass[i] && L.dinv_laplace[i] == op.laplace[i];
         double *cur = x.data(), *old = L.tmp.data();
         for (unsigned int k = 0; k < degree - 1; ++k)
           {
@@ -202,8 +208,8 @@ namespace spirk_host
                 rhok[i] = rhokp;
               }
             // x_new overwrites the x_old buffer (deal.II swaps solution / solution_old)
-            SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(), L.dinv.data(),
-                                           L.n, f1.data(), f2.data()));
+            SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
+                                           own_dinv ? nullptr : L.dinv.data(), L.n, f1.data(), f2.data()));
             std::swap(cur, old);
           }
         if (cur != x.data()) // odd number of steps: result sits in the tmp buffer
@@ -341,6 +347,12 @@ namespace spirk_host
           L.level = mg_operators[level]->get_matrix_free().level;
           L.n     = mg_operators[level]->get_matrix_free().n_dofs();
           mg_operators[level]->compute_inverse_diagonal(L.dinv);
+          const spirk_opdesc d = mg_operators[level]->descriptor();
+          if (d.kind == SPIRK_OP_REAL)
+            {
+              L.dinv_mass.assign(d.mass, d.mass + d.nb);
+              L.dinv_laplace.assign(d.laplace, d.laplace + d.nb);
+            }
         }
       for (unsigned int level = min_level; level <= max_level; ++level)
         estimate_eigenvalues(c, level, additional_data);
@@ -489,6 +501,8 @@ namespace spirk_host
               const auto &Lb = clones[b]->get_core().levels[l];
               L.dinv.block(b) = Lb.dinv;
               L.theta[b] = Lb.theta[0], L.delta[b] = Lb.delta[0];
+              if (Lb.dinv_mass.size() == 1)
+                L.dinv_mass.push_back(Lb.dinv_mass[0]), L.dinv_laplace.push_back(Lb.dinv_laplace[0]);
             }
         }
       const long long n0 = core.levels[0].n;

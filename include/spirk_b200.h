@@ -115,7 +115,9 @@ int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *o
 int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst,
                       const double *rhs, const double *src, long long stride);
 /* one Chebyshev iteration (deal.II PreconditionChebyshev, preconditioner.h:353-373):
- *   x_new = x + f1[b] (x - x_old) + f2[b] dinv .* (rhs - A x);  x_old == NULL means x_old = 0 */
+ *   x_new = x + f1[b] (x - x_old) + f2[b] dinv .* (rhs - A x);  x_old == NULL means x_old = 0;
+ *   dinv == NULL means "the inverse diagonal of op itself" (spirk_op_inverse_diagonal with op's
+ *   coefficients; REAL operators only) and saves reading that vector; x_new may alias x_old, not x */
 int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op,
                        double *x_new, const double *x, const double *x_old, const double *rhs,
                        const double *dinv, long long stride, const double *f1, const double *f2);

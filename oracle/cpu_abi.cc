@@ -548,6 +548,16 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
   ctx->scratch.resize((size_t)op->nb * N);
   if (int e = spirk_op_apply(ctx, lvl, op, ctx->scratch.data(), x, N))
     return e;
+  std::vector<double> own; // dinv == NULL: the operator's own inverse diagonal
+  if (!dinv)
+    {
+      if (op->kind != SPIRK_OP_REAL)
+        return fail(SPIRK_ERR_INVALID, "cheb_step: dinv == NULL needs a REAL operator");
+      own.resize((size_t)op->nb * stride);
+      for (int b = 0; b < op->nb; ++b)
+        spirk_op_inverse_diagonal(ctx, lvl, own.data() + b * stride, op->mass[b], op->laplace[b]);
+      dinv = own.data();
+    }
   for (int b = 0; b < op->nb; ++b)
     {
       const double *t = ctx->scratch.data() + b * N;

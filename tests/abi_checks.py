@@ -103,6 +103,14 @@ def check_residual_and_cheb(dev, dim, k, r, nb=2):
         new = ctx.download(dnew, x.shape)
         ref = (1 + f1[bc]) * x + f2[bc] * dinv * (b - Ax)
         assert relerr(new, ref) < RTOL
+        # dinv == NULL: the operator's own inverse diagonal, computed on the fly
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dnew, dx, dxo, db, None, olv.N, pf1, pf2)
+        new = ctx.download(dnew, x.shape)
+        ref = x + f1[bc] * (x - xo) + f2[bc] * dinv * (b - Ax)
+        assert relerr(new, ref) < RTOL
+        # x_new aliasing x_old (how the smoother calls it)
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dxo, dx, dxo, db, None, olv.N, pf1, pf2)
+        assert relerr(ctx.download(dxo, x.shape), ref) < RTOL
 
 
 def check_inverse_diagonal(dev, dim, k, r, mass=16.0, lap=0.1):

@@ -44,7 +44,10 @@ def main():
                 for name, fn, bytes_per_dof in [
                     ("apply", lambda: ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, N), 16),
                     ("cheb_step", lambda: ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dst, src, xo, rhs,
-                                                   dinv, N, f1, f2), 48),
+                                                   dinv, N, f1, f2), 40),
+                    ("cheb_step_own_dinv", lambda: ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dst, src, xo,
+                                                            rhs, None, N, f1, f2), 32),
+                    ("residual", lambda: ctx.call("spirk_op_residual", C.byref(lvl), C.byref(op), dst, rhs, src, N), 24),
                 ]:
                     for _ in range(3):
                         fn()
