@@ -381,19 +381,29 @@ namespace spirk_host
         {
           const double t0 = now_ns(src);
           const auto  &mf = p.op_level();
-          // K and M parts as two batched cell passes on the fused-epilogue fast path, then the A_inv
-          // coupling as one mixing kernel (with several ranks: after the all-gather of M v).  A single
-          // coupled cell pass (SPIRK_OP_COUPLED) computes the same in one sweep on the general kernel;
-          // it is kept for the complex operator.
-          {
-            std::vector<double> zero(p.m_local, 0.0), one(p.m_local, 1.0), tau(p.m_local, p.time_step);
-            const spirk_opdesc  dk = real_opdesc(p.m_local, zero.data(), tau.data());
-            const spirk_opdesc  dm = real_opdesc(p.m_local, one.data(), zero.data());
-            p.temp.reinit(src, true);
-            SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &dk, dst.data(), src.data(), src.block_size()));
-            SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &dm, p.temp.data(), src.data(), src.block_size()));
-            p.perform_basis_change(dst, p.temp, p.A_inv, true, 0.0);
-          }
+          if (p.row.size == 1)
+            {
+              spirk_opdesc d;
+              std::memset(&d, 0, sizeof(d));
+              d.kind = SPIRK_OP_COUPLED, d.nb = p.n_stages;
+              for (unsigned int i = 0; i < p.n_stages; ++i)
+                {
+                  d.laplace[i] = p.time_step;
+                  for (unsigned int j = 0; j < p.n_stages; ++j)
+                    d.coupling[i * p.n_stages + j] = p.A_inv(i, j);
+                }
+              SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &d, dst.data(), src.data(), src.block_size()));
+            }
+          else
+            {
+              std::vector<double> zero(p.m_local, 0.0), one(p.m_local, 1.0), tau(p.m_local, p.time_step);
+              const spirk_opdesc  dk = real_opdesc(p.m_local, zero.data(), tau.data());
+              const spirk_opdesc  dm = real_opdesc(p.m_local, one.data(), zero.data());
+              p.temp.reinit(src, true);
+              SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &dk, dst.data(), src.data(), src.block_size()));
+              SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &dm, p.temp.data(), src.data(), src.block_size()));
+              p.perform_basis_change(dst, p.temp, p.A_inv, true, 0.0);
+            }
           p.time_system_vmult += now_ns(src) - t0;
         }
       };
