@@ -265,8 +265,13 @@ def main():
         # x_new = 32 B (D^-1 is formed on the fly, A x never reaches memory); plain vmult reads src, writes dst = 16 B
         cheb_gbs = 32.0 * m * N / res["cheb_step"] * 1e-6
         vmult_gdofs = m * N / res["vmult"] * 1e-6
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):  # measured DRAM bytes / algorithmic bytes of this kernel (ncu --set full capture)
+            traffic = json.load(open(tpath))["traffic_over_algorithmic"] * 32.0 * m * N
         roof = {"bound": "hbm", "kernel": "fused Chebyshev step (cell operator + 3-term update), the smoother's kernel",
-                "achieved": cheb_gbs, "peak": peak, "unit": "GB/s", "frac": cheb_gbs / peak, "traffic": None,
+                "achieved": cheb_gbs, "peak": peak, "unit": "GB/s", "frac": cheb_gbs / peak, "traffic": traffic,
+                "traffic_note": "bytes per launch = (dram read+write)/algorithmic ratio of the ncu capture in profiles/ x this launch's algorithmic bytes",
                 "peak_source": peak_src, "algorithmic_bytes_per_dof": 32, "launch_ms": res["cheb_step"],
                 "vmult": {"achieved": 16.0 * vmult_gdofs, "frac": 16.0 * vmult_gdofs / peak, "launch_ms": res["vmult"],
                           "algorithmic_bytes_per_dof": 16}}
