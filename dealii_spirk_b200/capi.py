@@ -112,10 +112,14 @@ _SIGS = {
     "spirk_comm_allreduce_sum": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong],
     "spirk_comm_allgather": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong],
     "spirk_ctx_set_reduction_comm": [C.c_void_p, C.c_void_p],
+    "spirk_comm_xbuf_create": [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_void_p)],
+    "spirk_comm_xbuf_destroy": [C.c_void_p, C.c_void_p],
+    "spirk_mix_peer": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, dp,
+                       C.c_int, C.c_double],
 }
 # every symbol include/spirk_b200.h declares (tests check the library exports all of them)
 ALL_SYMBOLS = sorted(list(_SIGS) + ["spirk_backend", "spirk_last_error", "spirk_ctx_launch_count",
-                                    "spirk_level_n_dofs"])
+                                    "spirk_level_n_dofs", "spirk_comm_xbuf_local"])
 
 
 class DeviceLib:
@@ -133,6 +137,8 @@ class DeviceLib:
         self.lib.spirk_ctx_launch_count.restype = C.c_longlong
         self.lib.spirk_level_n_dofs.argtypes = [C.POINTER(Level)]
         self.lib.spirk_level_n_dofs.restype = C.c_longlong
+        self.lib.spirk_comm_xbuf_local.argtypes = [C.c_void_p]
+        self.lib.spirk_comm_xbuf_local.restype = C.c_void_p
 
     def backend(self):
         return self.lib.spirk_backend().decode()

@@ -311,6 +311,37 @@ namespace spirk
     }
   }
 
+  // fused all-gather + stage mixing over NVLink peer memory: input block j lives in the exchange
+  // buffer of rank j / m (peer-mapped pointer), block j % m; the loads of the remote blocks travel
+  // over NVLink while the q x q contraction runs (no gathered copy is ever written)
+  struct PeerPtrs
+  {
+    const double *p[SPIRK_MAX_BLOCKS];
+  };
+  template <int QI>
+  __global__ void k_mix_peer(const int qo, const int m, double *dst, const long long ds, const PeerPtrs peers,
+                             const long long n, const MixMatrix T, const int add)
+  {
+    SPIRK_GRID_STRIDE(e, n)
+    {
+      double in[QI];
+#pragma unroll
+      for (int j = 0; j < QI; ++j)
+        in[j] = peers.p[j / m][(long long)(j % m) * n + e];
+      for (int i = 0; i < qo; ++i)
+        {
+          double t = 0.0;
+#pragma unroll
+          for (int j = 0; j < QI; ++j)
+            t = fma(T.T[i * QI + j], in[j], t);
+          if (add)
+            dst[i * ds + e] += t;
+          else
+            dst[i * ds + e] = t;
+        }
+    }
+  }
+
   // =========================================================================================
   // problem pieces
   // =========================================================================================

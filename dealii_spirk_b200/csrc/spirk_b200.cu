@@ -863,6 +863,102 @@ int spirk_comm_allgather(spirk_ctx *ctx, spirk_comm *c, double *recv, const doub
   ctx->launches++;
   return SPIRK_OK;
 }
+// ---- peer-mapped exchange buffers + fused all-gather / mixing kernel
+struct spirk_xbuf
+{
+  double               *local = nullptr;
+  std::vector<double *> peer; // peer[r]: mapping of rank r's buffer (peer[rank] == local)
+  long long             n = 0;
+  int                   rank = 0, n_ranks = 1;
+  double               *d_sync = nullptr; // 1 double for the stream-ordered rank barrier
+};
+
+int spirk_comm_xbuf_create(spirk_ctx *ctx, spirk_comm *c, long long n, spirk_xbuf **out)
+{
+  if (c->n_ranks > SPIRK_MAX_BLOCKS)
+    return set_error(SPIRK_ERR_INVALID, "xbuf: too many ranks");
+  SPIRK_CUDA(cudaSetDevice(ctx->device));
+  spirk_xbuf *x = new spirk_xbuf();
+  x->n = n, x->rank = c->rank, x->n_ranks = c->n_ranks;
+  x->peer.assign(c->n_ranks, nullptr);
+  SPIRK_CUDA(cudaMalloc(&x->local, (size_t)n * sizeof(double)));
+  SPIRK_CUDA(cudaMemsetAsync(x->local, 0, (size_t)n * sizeof(double), ctx->stream));
+  SPIRK_CUDA(cudaMalloc(&x->d_sync, sizeof(double)));
+  SPIRK_CUDA(cudaMemsetAsync(x->d_sync, 0, sizeof(double), ctx->stream));
+  x->peer[c->rank] = x->local;
+  if (c->n_ranks > 1)
+    {
+      // exchange the IPC handles with an NCCL all-gather of bytes
+      cudaIpcMemHandle_t mine;
+      SPIRK_CUDA(cudaIpcGetMemHandle(&mine, x->local));
+      char *d_h = nullptr;
+      SPIRK_CUDA(cudaMalloc(&d_h, sizeof(mine) * (c->n_ranks + 1)));
+      SPIRK_CUDA(cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+      SPIRK_NCCL(nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), ncclChar, c->comm, ctx->stream));
+      std::vector<cudaIpcMemHandle_t> all(c->n_ranks);
+      SPIRK_CUDA(cudaMemcpyAsync(all.data(), d_h + sizeof(mine), sizeof(mine) * c->n_ranks, cudaMemcpyDeviceToHost, ctx->stream));
+      SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+      SPIRK_CUDA(cudaFree(d_h));
+      for (int r = 0; r < c->n_ranks; ++r)
+        if (r != c->rank)
+          {
+            void *p = nullptr;
+            SPIRK_CUDA(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+            x->peer[r] = (double *)p;
+          }
+    }
+  *out = x;
+  return SPIRK_OK;
+}
+
+int spirk_comm_xbuf_destroy(spirk_ctx *ctx, spirk_xbuf *x)
+{
+  if (!x)
+    return SPIRK_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int r = 0; r < x->n_ranks; ++r)
+    if (r != x->rank && x->peer[r])
+      cudaIpcCloseMemHandle(x->peer[r]);
+  cudaFree(x->local);
+  cudaFree(x->d_sync);
+  delete x;
+  return SPIRK_OK;
+}
+
+double *spirk_comm_xbuf_local(spirk_xbuf *x) { return x->local; }
+
+int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, double *dst, long long ds, long long n,
+                   const double *T, int add, double cutoff)
+{
+  const int qi = c->n_ranks * m;
+  if (qo < 1 || qi > SPIRK_MAX_BLOCKS || qo > SPIRK_MAX_BLOCKS || (long long)m * n > x->n)
+    return set_error(SPIRK_ERR_INVALID, "mix_peer: block counts / buffer size");
+  MixMatrix M;
+  for (int i = 0; i < qo; ++i)
+    for (int j = 0; j < qi; ++j)
+      M.T[i * qi + j] = (std::fabs(T[i * qi + j]) > cutoff) ? T[i * qi + j] : 0.0;
+  PeerPtrs pp;
+  for (int r = 0; r < c->n_ranks; ++r)
+    pp.p[r] = x->peer[r];
+  // stream-ordered rank barrier: every rank has finished writing its exchange buffer
+  if (c->n_ranks > 1)
+    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  const int grid = grid_for(ctx, n, 256);
+#define MIXP_CASE(Q) \
+  case Q: k_mix_peer<Q><<<grid, 256, 0, ctx->stream>>>(qo, m, dst, ds, pp, n, M, add); break;
+  switch (qi)
+    {
+      MIXP_CASE(1) MIXP_CASE(2) MIXP_CASE(3) MIXP_CASE(4) MIXP_CASE(5) MIXP_CASE(6) MIXP_CASE(7) MIXP_CASE(8)
+      MIXP_CASE(9) MIXP_CASE(10) MIXP_CASE(11) MIXP_CASE(12) MIXP_CASE(13) MIXP_CASE(14) MIXP_CASE(15) MIXP_CASE(16)
+    }
+  SPIRK_LAUNCH_CHECK(ctx);
+  // ... and every rank has finished reading before a buffer may be overwritten
+  if (c->n_ranks > 1)
+    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  return SPIRK_OK;
+}
+
 int spirk_ctx_set_reduction_comm(spirk_ctx *ctx, spirk_comm *comm)
 {
   ctx->reduction_comm = comm;

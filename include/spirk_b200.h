@@ -200,6 +200,21 @@ int spirk_comm_allreduce_sum(spirk_ctx *ctx, spirk_comm *comm, double *buf, long
 /* recv[r*n .. r*n+n) = send of rank r (replaces the MPI_Sendrecv_replace ring, main.cc:1465-1483) */
 int spirk_comm_allgather(spirk_ctx *ctx, spirk_comm *comm, double *recv, const double *send,
                          long long n);
+/* Peer-mapped exchange buffers over NVLink / NVSwitch (collective): every rank allocates n doubles and
+ * maps the buffers of all other ranks (CUDA IPC), the analogue of the reference's MPI-3 shared-memory
+ * window (main.cc:1327-1331, 229-235, `UseSharedMemory`). */
+typedef struct spirk_xbuf spirk_xbuf;
+int     spirk_comm_xbuf_create(spirk_ctx *ctx, spirk_comm *comm, long long n, spirk_xbuf **xbuf);
+int     spirk_comm_xbuf_destroy(spirk_ctx *ctx, spirk_xbuf *xbuf);
+double *spirk_comm_xbuf_local(spirk_xbuf *xbuf); /* this rank's buffer (device pointer) */
+/* Fused all-gather + stage mixing in ONE kernel over peer memory (collective):
+ *   dst_i = [dst_i +] sum_j T[i*q+j] * X_j,  i < q_out,  q = n_ranks * m_per_rank,
+ * where X_j is block (j % m_per_rank) (stride n) of rank (j / m_per_rank)'s exchange buffer, read
+ * directly over NVLink (peer loads) — the `use_sm` variant of perform_basis_change,
+ * main.cc:1506-1533.  Ranks are synchronised on the stream before and after the peer reads, so the
+ * exchange buffer may be overwritten as soon as the call returns (in stream order). */
+int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *comm, spirk_xbuf *xbuf, int q_out, int m_per_rank, double *dst,
+                   long long dst_stride, long long n, const double *host_T, int add, double cutoff);
 /* attach / detach (NULL) the communicator over which dot products are summed */
 int spirk_ctx_set_reduction_comm(spirk_ctx *ctx, spirk_comm *comm);
 

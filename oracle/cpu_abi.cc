@@ -1047,6 +1047,35 @@ int spirk_comm_allgather(spirk_ctx *, spirk_comm *c, double *recv, const double 
     std::memcpy(recv, send, n * sizeof(double));
   return SPIRK_OK;
 }
+struct spirk_xbuf
+{
+  std::vector<double> local;
+};
+int spirk_comm_xbuf_create(spirk_ctx *, spirk_comm *, long long n, spirk_xbuf **out)
+{
+  *out = new spirk_xbuf();
+  (*out)->local.assign((size_t)n, 0.0);
+  return SPIRK_OK;
+}
+int spirk_comm_xbuf_destroy(spirk_ctx *, spirk_xbuf *x)
+{
+  delete x;
+  return SPIRK_OK;
+}
+double *spirk_comm_xbuf_local(spirk_xbuf *x) { return x->local.data(); }
+// the CPU double has no peer memory: all-gather through the registered callback, then mix locally
+int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, double *dst, long long ds, long long n,
+                   const double *T, int add, double cutoff)
+{
+  const int           qi = c->n_ranks * m;
+  std::vector<double> all((size_t)qi * n);
+  std::vector<double> mine((size_t)m * n);
+  for (int b = 0; b < m; ++b)
+    std::memcpy(&mine[(size_t)b * n], &x->local[(size_t)b * n], n * sizeof(double));
+  if (int e = spirk_comm_allgather(ctx, c, all.data(), mine.data(), (long long)m * n))
+    return e;
+  return spirk_mix(ctx, qo, qi, dst, ds, all.data(), n, n, T, add, cutoff);
+}
 int spirk_ctx_set_reduction_comm(spirk_ctx *, spirk_comm *c)
 {
   g_reduction_comm = c;
