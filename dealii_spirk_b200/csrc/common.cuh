@@ -21,6 +21,7 @@ namespace spirk
     double Be[(SPIRK_MAX_DEGREE + 2) * SPIRK_MAX_N];      // [(q)*n+i]
     double xe[SPIRK_MAX_DEGREE + 2], we[SPIRK_MAX_DEGREE + 2];
     double nodes[SPIRK_MAX_N];
+    double Mv, Kv; // assembled 1-D diagonals at a vertex node shared by two cells: Mh[k][k] + Mh[0][0]
   };
 
   // geometry handed to kernels by value

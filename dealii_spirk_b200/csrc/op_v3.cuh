@@ -1,0 +1,566 @@
+// Matrix-free cell operator, variant 3: owner-computes plane streaming (3-D, uniform Cartesian mesh).
+//
+// The operator on the refined hypercube is a sum of Kronecker products of the GLOBAL banded 1-D
+// matrices (assembled from the reference cell matrices Mh, Kh):
+//   A = cm Mz My Mx + cl (Mz My Kx + Mz Ky Mx + Kz My Mx),   cm = mass h^3, cl = laplace h
+// which factors into 7 one-dimensional banded sweeps
+//   x :  a' = cl Mx u,             c = (cm Mx + cl Kx) u
+//   y :  p' = My a',               w = My c + Ky a'
+//   z :  out = Mz w + Kz p'
+// A row of a banded 1-D matrix has 2k+1 entries at a vertex node (shared by two cells) and k+1 at a
+// cell-interior node: 6 FMA per node and sweep at k = 4, about 44 FMA per DoF in total.
+//
+// Work decomposition.  A CTA owns a column of TX x TY cells (k TX x k TY node columns, "owner
+// computes": nodes [k TX tx, k TX (tx+1)) x [k TY ty, ...)) and streams it upwards in z one NODE
+// PLANE at a time through a ring of shared-memory slots:
+//   stage   : every row of the (k TX + k + 1) x (k TY + k + 1) staged nodes of `src` (owned + one
+//             cell of halo below, one node above) is ONE bulk-async copy (cp.async.bulk = TMA 1-D,
+//             completion on an mbarrier), issued two planes ahead; rows start at arbitrary 8-byte
+//             parity (n1 is odd), so a copy starts at the 16-byte aligned address below the row and
+//             the consumers add the parity.  The rows of the epilogue operands (rhs, x_old) of the
+//             same plane travel in the same slot.  No thread ever waits on a global load.
+//   x-phase : one thread per (staged row, cell segment): 2k+1 loads, the k owned outputs of a', c.
+//             Dirichlet / out-of-domain nodes are masked here (rows, planes and the two x-columns).
+//   y+z     : one thread per (owned x, cell segment in y), lanes along x: 2(2k+1) loads, the k owned
+//             outputs of p', w, and IMMEDIATELY their contribution to the z-sums of the current
+//             cell layer, which live in registers ((k+1) planes x k nodes).  The linear part of the
+//             fused epilogue (residual: rhs; Chebyshev: x, x_old, rhs) is folded into the z-sums
+//             when the plane passes, so when the top plane of a layer has been added, planes 0..k-1
+//             are final up to one scaling and are stored straight from registers, 256-byte
+//             coalesced per warp.  The top plane's sums carry over to the next layer.
+// No partial sums ever leave the SM: no atomics, no zero-init pass, no wall/exchange arrays, no
+// second kernel; results are bitwise reproducible.  The price is the halo: (37/32)^2 of the plane
+// is staged and 37/32 of the x-sweeps are computed for an 8 x 8-cell tile.
+// The (block, column, layer) space is split evenly over a fixed grid of 2 CTAs per SM; a piece that
+// starts above layer 0 recomputes the layer below it to obtain its incoming z-sums.
+//
+// Replaces the deal.II cell loop + vector updates of the reference:
+//   operator.h:298-310, 379-421 (vmult), 841-880 (batched); deal.II PreconditionChebyshev
+//   vector_updates and the residual of Multigrid::level_v_step (A8).
+#pragma once
+#include <cstdint>
+
+#include "op_v2.cuh"
+
+namespace spirk
+{
+  __host__ __device__ constexpr int v3_nops(const int mode) { return mode == V2_RESIDUAL ? 1 : (mode == V2_CHEB_OWN ? 2 : 0); }
+
+  template <int K, int TX, int TY, int MODE>
+  struct CfgV3
+  {
+    static constexpr int n = K + 1, OX = K * TX, OY = K * TY, LXS = OX + K + 1, LYS = OY + K + 1;
+    static constexpr int PUP  = (LXS + 2) & ~1; // staged row incl. the parity shift, whole 16-byte chunks
+    static constexpr int POP  = OX + 2;         // operand row incl. the parity shift
+    static constexpr int PA   = OX | 1;         // odd pitch: lanes along y hit distinct banks
+    static constexpr int NOPS = v3_nops(MODE);  // operand planes that travel with the staged plane
+    static constexpr int NBUF = 3;              // ring depth (two planes in flight)
+    static constexpr int NAC  = (NOPS == 2) ? 1 : 2; // a'/c tile double-buffered where shared memory allows
+    static constexpr int SLOT = LYS * PUP + NOPS * OY * POP;
+    static constexpr int NT   = OX * TY; // threads = y+z tasks
+    static constexpr int NXT  = LYS * TX; // x-phase tasks
+    static constexpr int NROWS = LYS + NOPS * OY; // bulk copies per plane
+    static constexpr int MINB = (NT >= 256) ? 2 : (NT >= 128 ? 4 : 8);
+    static constexpr unsigned ROWB_U = PUP * 8, ROWB_O = POP * 8;
+    static constexpr size_t   smem = sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
+    static_assert(NT % 32 == 0 && NT <= 1024 && NROWS <= NT, "tile shape");
+    static_assert(PUP % 2 == 0 && POP % 2 == 0 && SLOT % 2 == 0 && (LYS * PUP) % 2 == 0, "16-byte aligned rows");
+  };
+
+  // Mh / Kh are symmetric and persymmetric (made exact at upload): index the canonical copy of an entry so
+  // that the compiler loads each distinct value once (FP64 instructions take no constant-bank operands)
+  template <int K>
+  __host__ __device__ constexpr int v3_canon(const int i, const int j)
+  {
+    int a = i < j ? i : j, b = i < j ? j : i;
+    const int a2 = K - b, b2 = K - a;
+    if (a2 < a || (a2 == a && b2 < b))
+      a = a2, b = b2;
+    return a * (K + 1) + b;
+  }
+
+  struct V3Args
+  {
+    Geo           g;
+    int           nb;
+    long long     stride;
+    double       *dst;
+    const double *src, *x_old, *rhs, *dinv;
+    double        cm[SPIRK_MAX_BLOCKS], cl[SPIRK_MAX_BLOCKS], f1[SPIRK_MAX_BLOCKS], f2[SPIRK_MAX_BLOCKS];
+    int           ntx, nty;
+    long long     W; // nb * columns * layers
+  };
+
+  __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+  __device__ __forceinline__ void     mbar_init(const unsigned bar, const int count)
+  {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+  }
+  __device__ __forceinline__ void mbar_arrive_expect_tx(const unsigned bar, const unsigned bytes)
+  {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+  }
+  __device__ __forceinline__ bool mbar_try_wait(const unsigned bar, const unsigned parity)
+  {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    return ok != 0;
+  }
+  // bulk-async (TMA) 1-D copy global -> shared, completion counted in bytes on an mbarrier
+  __device__ __forceinline__ void bulk_g2s(const unsigned dst, const void *src, const unsigned bytes, const unsigned bar)
+  {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+  }
+
+  // identity rows (Dirichlet nodes): A x = x
+  template <int MODE>
+  __device__ __forceinline__ void v3_identity(const V3Args &a, const double f1, const double f2, const long long j)
+  {
+    const double x = a.src[j];
+    if (MODE == V2_APPLY)
+      a.dst[j] = x;
+    else if (MODE == V2_RESIDUAL)
+      a.dst[j] = a.rhs[j] - x;
+    else
+      {
+        const double xo = a.x_old ? a.x_old[j] : 0.0;
+        const double di = (MODE == V2_CHEB) ? a.dinv[j] : 1.0;
+        a.dst[j]        = fma(f2 * di, a.rhs[j] - x, fma(f1, x - xo, x));
+      }
+  }
+
+  template <int K, int TX, int TY, int MODE>
+  __global__ void __launch_bounds__(CfgV3<K, TX, TY, MODE>::NT, CfgV3<K, TX, TY, MODE>::MINB) k_v3(const V3Args a)
+  {
+    using C = CfgV3<K, TX, TY, MODE>;
+    constexpr int n = C::n, OX = C::OX, OY = C::OY, LYS = C::LYS, PUP = C::PUP, POP = C::POP, PA = C::PA, NT = C::NT;
+    constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT;
+    extern __shared__ __align__(16) double sm3[];
+    double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K;
+    uint64_t *BAR  = reinterpret_cast<uint64_t *>(SDI + K * K * K);
+    const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
+    const double  Mv = c_fe[K].Mv, Kv = c_fe[K].Kv;
+#define MC(i, j) Mh[v3_canon<K>(i, j)]
+#define KC(i, j) Kh[v3_canon<K>(i, j)]
+
+    const int       tid = threadIdx.x;
+    const int       n1 = a.g.n1, nc = a.g.nc;
+    const long long plane = (long long)n1 * n1;
+    const int       ncols = a.ntx * a.nty;
+    const int       xl = tid % OX, ys = tid / OX; // y+z task: owned x, cell segment in y
+
+    if (tid == 0)
+      {
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i)
+          mbar_init(smem_u32(BAR + i), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      }
+    const unsigned ring_u32 = smem_u32(RING), bar_u32 = smem_u32(BAR);
+
+    long long       w     = a.W * blockIdx.x / gridDim.x;
+    const long long w_end = a.W * (blockIdx.x + 1) / gridDim.x;
+    int             b_tab = -1;
+    unsigned        it0   = 0; // ring position of the piece's first plane (runs on across pieces)
+    while (w < w_end)
+      {
+        // ------------------------------------------------------------------ decode the piece
+        const int       L0  = (int)(w % nc);
+        const long long t_  = w / nc;
+        const int       col = (int)(t_ % ncols), b = (int)(t_ / ncols);
+        const int       L1  = (int)min((long long)nc, L0 + (w_end - w));
+        w += L1 - L0;
+        const int       tx = col % a.ntx, ty = col / a.ntx;
+        const int       gx0 = tx * OX, gy0 = ty * OY;
+        const double    cm = a.cm[b], cl = a.cl[b], f1 = a.f1[b], f2 = a.f2[b];
+        const long long boff = (long long)b * a.stride;
+        const double   *src  = a.src + boff;
+        const int       zf   = (L0 > 0) ? L0 - 1 : 0;      // first layer that is processed (recomputed if < L0)
+        const int       nsteps = 1 + K * (L1 - zf);        // node planes K zf .. K L1
+        const bool      has_xo = (a.x_old != nullptr);
+
+        __syncthreads(); // the previous piece is finished with the ring, the a'/c tile and the tables
+        if (MODE == V2_CHEB_OWN && b != b_tab)
+          {
+            // scaling by node class (position of the node inside its cell): -f2 / diag and its inverse
+            for (int e = tid; e < K * K * K; e += NT)
+              {
+                const int    cx = e % K, cy = (e / K) % K, cz = e / (K * K);
+                const double mx = cx ? Mh[cx * n + cx] : Mv, kx = cx ? Kh[cx * n + cx] : Kv;
+                const double my = cy ? Mh[cy * n + cy] : Mv, ky = cy ? Kh[cy * n + cy] : Kv;
+                const double mz = cz ? Mh[cz * n + cz] : Mv, kz = cz ? Kh[cz * n + cz] : Kv;
+                const double d  = cm * mx * my * mz + cl * (kx * my * mz + mx * ky * mz + mx * my * kz);
+                const double di = (fabs(d) > 1.0e-10) ? 1.0 / d : 1.0;
+                SDS[e] = -f2 * di, SDI[e] = 1.0 / (f2 * di);
+              }
+            b_tab = b;
+          }
+
+        // ------------------------------------------------------------------ this thread's bulk copy of a plane
+        // tid < LYS: staged row tid of src; then OY rows of operand 0 (x_old | rhs), then OY rows of operand 1 (rhs)
+        const double *my_base  = nullptr;
+        unsigned      my_soff  = 0, my_bytes = 0;
+        bool          my_is_op = false;
+        int           nvalid_u = 0; // staged rows inside the domain and off the Dirichlet boundary
+        {
+          for (int r = 0; r < LYS; ++r)
+            {
+              const int gy = gy0 - K + r;
+              nvalid_u += (gy > 0 && gy < n1 - 1) ? 1 : 0;
+            }
+          if (tid < LYS)
+            {
+              const int gy = gy0 - K + tid;
+              if (gy > 0 && gy < n1 - 1)
+                my_base = src + (gx0 - K) + (long long)n1 * gy;
+              my_soff = tid * PUP * 8, my_bytes = C::ROWB_U;
+            }
+          else if (NOPS > 0 && tid < C::NROWS)
+            {
+              const int     o  = (tid - LYS) / OY, ro = (tid - LYS) % OY;
+              const double *ob = (MODE == V2_RESIDUAL) ? a.rhs : (o == 0 ? a.x_old : a.rhs);
+              if (ob != nullptr)
+                my_base = ob + boff + gx0 + (long long)n1 * (gy0 + ro);
+              my_soff = (LYS * PUP + (o * OY + ro) * POP) * 8, my_bytes = C::ROWB_O, my_is_op = true;
+            }
+        }
+        const unsigned op_bytes = (MODE == V2_RESIDUAL) ? OY * C::ROWB_O : (NOPS == 2 ? (has_xo ? 2 : 1) * OY * C::ROWB_O : 0);
+        auto           issue    = [&](const int sidx) {
+          const int      P     = K * zf + sidx;
+          const unsigned slot  = (it0 + sidx) % NBUF;
+          const bool     zpl   = (P <= 0) || (P >= n1 - 1);
+          const bool     owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+          if (tid == 0)
+            mbar_arrive_expect_tx(bar_u32 + 8 * slot, (zpl ? 0u : nvalid_u * C::ROWB_U) + (owned ? op_bytes : 0u));
+          if (my_base != nullptr && (my_is_op ? owned : !zpl))
+            {
+              const uintptr_t p = reinterpret_cast<uintptr_t>(my_base + plane * P) & ~(uintptr_t)15;
+              bulk_g2s(ring_u32 + slot * (SLOT * 8) + my_soff, reinterpret_cast<const void *>(p), my_bytes, bar_u32 + 8 * slot);
+            }
+        };
+        // parities (n1 is odd: a row / plane step flips the 8-byte parity of the row start)
+        const int par_u  = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1) + gx0 - K + gy0 - K + K * zf;
+        const int par_o0 = (NOPS > 0) ? (int)((reinterpret_cast<uintptr_t>((MODE == V2_RESIDUAL ? a.rhs : a.x_old) + boff) >> 3) & 1) + gx0 + gy0 + K * zf : 0;
+        const int par_o1 = (NOPS > 1) ? (int)((reinterpret_cast<uintptr_t>(a.rhs + boff) >> 3) & 1) + gx0 + gy0 + K * zf : 0;
+
+        double acc[n][K]; // z-sums of the current layer: planes 0..K x the K owned nodes of this thread
+#pragma unroll
+        for (int z = 0; z < n; ++z)
+#pragma unroll
+          for (int i = 0; i < K; ++i)
+            acc[z][i] = 0.0;
+
+        for (int s = 0; s < NBUF && s < nsteps; ++s)
+          issue(s);
+        for (int s = 0; s < nsteps; ++s)
+          {
+            const unsigned slot = (it0 + s) % NBUF;
+            const int      P    = K * zf + s;
+            const bool     zpl  = (P <= 0) || (P >= n1 - 1);
+            const double  *ub   = RING + slot * SLOT;
+            double        *SA = AC + (NAC == 2 ? (s & 1) * (2 * LYS * PA) : 0), *SC = SA + LYS * PA;
+            while (!mbar_try_wait(bar_u32 + 8 * slot, ((it0 + s) / NBUF) & 1))
+              ;
+            if (NAC == 1)
+              __syncthreads(); // the a'/c tile of the previous plane is consumed
+
+            // -------------------------------------------------------------- x-phase
+            for (int q = tid; q < C::NXT; q += NT)
+              {
+                const int seg = q / LYS, row = q - seg * LYS;
+                const int gy  = gy0 - K + row;
+                double   *oa = SA + row * PA + K * seg, *oc = SC + row * PA + K * seg;
+                if (zpl || gy <= 0 || gy >= n1 - 1)
+                  {
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      oa[i] = 0.0, oc[i] = 0.0;
+                  }
+                else
+                  {
+                    const double *ur = ub + row * PUP + ((par_u + row + s) & 1) + K * seg;
+                    double        u[2 * K + 1];
+#pragma unroll
+                    for (int j = 0; j < 2 * K + 1; ++j)
+                      u[j] = ur[j];
+                    if (seg == 0 && tx == 0)
+                      { // x < 0 (outside) and x = 0 (Dirichlet)
+#pragma unroll
+                        for (int j = 0; j <= K; ++j)
+                          u[j] = 0.0;
+                      }
+                    if (seg == 1 && tx == 0)
+                      u[0] = 0.0; // x = 0 seen from the second cell
+                    if (seg == TX - 1 && tx == a.ntx - 1)
+                      u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
+                    double am[K], ak[K];
+                    am[0] = Mv * u[K], ak[0] = Kv * u[K];
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+                      am[0] = fma(MC(K, j), u[j], am[0]), ak[0] = fma(KC(K, j), u[j], ak[0]);
+#pragma unroll
+                    for (int j = 1; j <= K; ++j)
+                      am[0] = fma(MC(0, j), u[K + j], am[0]), ak[0] = fma(KC(0, j), u[K + j], ak[0]);
+#pragma unroll
+                    for (int i = 1; i < K; ++i)
+                      {
+                        am[i] = MC(i, 0) * u[K], ak[i] = KC(i, 0) * u[K];
+#pragma unroll
+                        for (int j = 1; j <= K; ++j)
+                          am[i] = fma(MC(i, j), u[K + j], am[i]), ak[i] = fma(KC(i, j), u[K + j], ak[i]);
+                      }
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      oa[i] = cl * am[i], oc[i] = fma(cm, am[i], cl * ak[i]);
+                  }
+              }
+            __syncthreads();
+            // the slot of the previous plane is free now (its operands were read in the previous y+z phase)
+            if (s >= 1 && s - 1 + NBUF < nsteps)
+              issue(s - 1 + NBUF);
+
+            // -------------------------------------------------------------- y-sweep
+            double p[K], wv[K];
+            {
+              const double *ar = SA + (K * ys) * PA + xl, *cr = SC + (K * ys) * PA + xl;
+              double        av[2 * K + 1], cv[2 * K + 1];
+#pragma unroll
+              for (int j = 0; j < 2 * K + 1; ++j)
+                av[j] = ar[j * PA], cv[j] = cr[j * PA];
+              p[0]  = Mv * av[K];
+              wv[0] = fma(Kv, av[K], Mv * cv[K]);
+#pragma unroll
+              for (int j = 0; j < K; ++j)
+                {
+                  p[0]  = fma(MC(K, j), av[j], p[0]);
+                  wv[0] = fma(MC(K, j), cv[j], fma(KC(K, j), av[j], wv[0]));
+                }
+#pragma unroll
+              for (int j = 1; j <= K; ++j)
+                {
+                  p[0]  = fma(MC(0, j), av[K + j], p[0]);
+                  wv[0] = fma(MC(0, j), cv[K + j], fma(KC(0, j), av[K + j], wv[0]));
+                }
+#pragma unroll
+              for (int i = 1; i < K; ++i)
+                {
+                  p[i]  = MC(i, 0) * av[K];
+                  wv[i] = fma(KC(i, 0), av[K], MC(i, 0) * cv[K]);
+#pragma unroll
+                  for (int j = 1; j <= K; ++j)
+                    {
+                      p[i]  = fma(MC(i, j), av[K + j], p[i]);
+                      wv[i] = fma(MC(i, j), cv[K + j], fma(KC(i, j), av[K + j], wv[i]));
+                    }
+                }
+            }
+            // -------------------------------------------------------------- linear part of the epilogue of this plane
+            // g = rhs (residual) | rhs + ((1 + f1) x - f1 x_old) / (f2 dinv) (Chebyshev); the z-sums run on A x - g
+            const int  zl    = (s == 0) ? 0 : ((s - 1) % K) + 1;
+            const bool owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+            double     g[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i)
+              g[i] = 0.0;
+            if (NOPS > 0 && owned)
+              {
+                if (MODE == V2_RESIDUAL)
+                  {
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      g[i] = ub[LYS * PUP + (K * ys + i) * POP + xl + ((par_o0 + K * ys + i + s) & 1)];
+                  }
+                else
+                  {
+                    const double *o1  = ub + LYS * PUP + (OY + K * ys) * POP + xl;
+                    const double *ux  = ub + (K + K * ys) * PUP + K + xl;
+                    const double *sdi = SDI + ((P % K) * K) * K + (xl % K);
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      {
+                        const double x   = ux[i * PUP + ((par_u + K + K * ys + i + s) & 1)];
+                        const double xo  = has_xo ? ub[LYS * PUP + (K * ys + i) * POP + xl + ((par_o0 + K * ys + i + s) & 1)] : 0.0;
+                        const double rh  = o1[i * POP + ((par_o1 + K * ys + i + s) & 1)];
+                        g[i]             = fma(fma(f1, x - xo, x), sdi[i * K], rh);
+                      }
+                  }
+              }
+            // -------------------------------------------------------------- z-accumulation
+            if (zl < K)
+              {
+                // columns 0..K-1 of the cell matrices (uniform switch keeps the entries in few registers)
+#pragma unroll
+                for (int zz = 0; zz < K; ++zz)
+                  if (zl == zz)
+                    {
+#pragma unroll
+                      for (int z = 0; z < n; ++z)
+#pragma unroll
+                        for (int i = 0; i < K; ++i)
+                          acc[z][i] = fma(MC(z, zz), wv[i], fma(KC(z, zz), p[i], acc[z][i]));
+                      if (NOPS > 0 && zz > 0)
+                        {
+#pragma unroll
+                          for (int i = 0; i < K; ++i)
+                            acc[zz][i] -= g[i];
+                        }
+                    }
+              }
+            else
+              {
+                const int Lc = zf + (s - 1) / K; // the layer that this (top) plane completes
+#pragma unroll
+                for (int z = 0; z < n; ++z)
+#pragma unroll
+                  for (int i = 0; i < K; ++i)
+                    acc[z][i] = fma(MC(z, K), wv[i], fma(KC(z, K), p[i], acc[z][i]));
+                if (Lc >= L0)
+                  {
+                    const int       gx = gx0 + xl, gy = gy0 + K * ys;
+                    const long long j0 = boff + gx + (long long)n1 * gy + plane * (K * Lc);
+                    const bool      anyb = (gx == 0) || (gy == 0) || (Lc == 0);
+                    if (MODE == V2_CHEB)
+                      {
+                        // explicit inverse diagonal: operands straight from global memory
+#pragma unroll
+                        for (int z = 0; z < K; ++z)
+#pragma unroll
+                          for (int i = 0; i < K; ++i)
+                            {
+                              const long long j = j0 + z * plane + i * n1;
+                              if (anyb && ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0)))
+                                v3_identity<MODE>(a, f1, f2, j);
+                              else
+                                {
+                                  const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
+                                  a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - acc[z][i], fma(f1, x - xo, x));
+                                }
+                            }
+                      }
+                    else
+                      {
+                        double       *dp  = a.dst + j0;
+                        const double *sds = SDS + (xl % K);
+                        if (!anyb)
+                          {
+#pragma unroll
+                            for (int z = 0; z < K; ++z)
+#pragma unroll
+                              for (int i = 0; i < K; ++i)
+                                dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
+                                                         : (MODE == V2_RESIDUAL) ? -acc[z][i]
+                                                                                 : sds[(z * K + i) * K] * acc[z][i];
+                          }
+                        else
+                          {
+#pragma unroll
+                            for (int z = 0; z < K; ++z)
+#pragma unroll
+                              for (int i = 0; i < K; ++i)
+                                {
+                                  if ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0))
+                                    v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1);
+                                  else
+                                    dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
+                                                             : (MODE == V2_RESIDUAL) ? -acc[z][i]
+                                                                                     : sds[(z * K + i) * K] * acc[z][i];
+                                }
+                          }
+                      }
+                    // Dirichlet faces x = n1-1 and y = n1-1 of these K planes (owned by no tile)
+                    if (tx == a.ntx - 1)
+                      {
+                        const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
+                        for (int e = tid; e < K * oye; e += NT)
+                          v3_identity<MODE>(a, f1, f2,
+                                            boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye));
+                      }
+                    if (ty == a.nty - 1)
+                      for (int e = tid; e < K * OX; e += NT)
+                        v3_identity<MODE>(a, f1, f2,
+                                          boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
+                  }
+                // the top plane becomes the bottom plane of the next layer
+#pragma unroll
+                for (int i = 0; i < K; ++i)
+                  {
+                    acc[0][i] = fma(MC(0, 0), wv[i], fma(KC(0, 0), p[i], acc[K][i])) - g[i];
+#pragma unroll
+                    for (int z = 1; z < n; ++z)
+                      acc[z][i] = fma(MC(z, 0), wv[i], KC(z, 0) * p[i]);
+                  }
+              }
+          }
+        it0 += nsteps;
+        // top plane of the domain (Dirichlet)
+        if (L1 == nc)
+          {
+            const int oxe = OX + (tx == a.ntx - 1 ? 1 : 0), oye = OY + (ty == a.nty - 1 ? 1 : 0);
+            for (int e = tid; e < oxe * oye; e += NT)
+              v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % oxe) + (long long)n1 * (gy0 + e / oxe) + plane * (n1 - 1));
+          }
+      }
+#undef MC
+#undef KC
+  }
+
+  template <int K, int TX, int TY, int MODE>
+  int v3_launch_mode(spirk_ctx *ctx, const V3Args &a)
+  {
+    using C = CfgV3<K, TX, TY, MODE>;
+    static bool attr_set = false;
+    if (!attr_set)
+      {
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+        attr_set = true;
+      }
+    // fixed grid: all co-resident CTAs, but no piece shorter than ~4 layers (a piece above layer 0
+    // recomputes one layer)
+    const long long slots = (long long)ctx->n_sms * C::MINB;
+    const long long grid  = std::max(1LL, std::min(slots, a.W / 4));
+    k_v3<K, TX, TY, MODE><<<(unsigned int)grid, C::NT, C::smem, ctx->stream>>>(a);
+    SPIRK_LAUNCH_CHECK(ctx);
+    return SPIRK_OK;
+  }
+
+  template <int K, int TX, int TY>
+  int v3_launch(spirk_ctx *ctx, V3Args &a, const V2Mode mode)
+  {
+    a.ntx = a.g.nc / TX, a.nty = a.g.nc / TY;
+    a.W   = (long long)a.nb * a.ntx * a.nty * a.g.nc;
+    if (mode == V2_APPLY)
+      return v3_launch_mode<K, TX, TY, V2_APPLY>(ctx, a);
+    if (mode == V2_RESIDUAL)
+      return v3_launch_mode<K, TX, TY, V2_RESIDUAL>(ctx, a);
+    if (a.dinv != nullptr)
+      return v3_launch_mode<K, TX, TY, V2_CHEB>(ctx, a);
+    return v3_launch_mode<K, TX, TY, V2_CHEB_OWN>(ctx, a);
+  }
+
+  // returns SPIRK_ERR_UNSUPPORTED when the level / operator shape is not covered
+  inline int v3_apply(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, V2Mode mode, double *dst, const double *src,
+                      const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
+                      const double *f2)
+  {
+    if (g.dim != 3 || g.k != 4 || op->kind != SPIRK_OP_REAL || g.nc % 8 != 0 || g.nc < 8)
+      return SPIRK_ERR_UNSUPPORTED;
+    V3Args a;
+    a.g = g, a.nb = op->nb, a.stride = stride;
+    a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = dinv;
+    const double hd = g.h * g.h * g.h, hl = g.h;
+    for (int b = 0; b < op->nb; ++b)
+      {
+        a.cm[b] = op->mass[b] * hd, a.cl[b] = op->laplace[b] * hl;
+        a.f1[b] = f1 ? f1[b] : 0.0, a.f2[b] = f2 ? f2[b] : 0.0;
+        if (mode >= V2_CHEB && dinv == nullptr && a.f2[b] == 0.0)
+          return SPIRK_ERR_UNSUPPORTED; // the folded Chebyshev epilogue divides by f2
+      }
+    return v3_launch<4, 8, 8>(ctx, a, mode);
+  }
+} // namespace spirk

@@ -9,7 +9,7 @@
 #include "fe1d.h"
 #include "misc_kernels.cuh"
 #include "nccl_dl.h"
-#include "op_v2.cuh"
+#include "op_v3.cuh"
 
 namespace spirk
 {
@@ -44,8 +44,14 @@ namespace spirk
       {
         const Fe1D &f = g_fe[k];
         const int   n = f.n;
-        for (int i = 0; i < n * n; ++i)
-          all[k].Mh[i] = f.Mh[i], all[k].Kh[i] = f.Kh[i];
+        // the reference matrices are persymmetric (the GLL nodes are symmetric about the cell centre); make
+        // that exact in the device copy so kernels may share the value of mirrored entries (op_v3.cuh)
+        for (int i = 0; i < n; ++i)
+          for (int j = 0; j < n; ++j)
+            {
+              all[k].Mh[i * n + j] = 0.5 * (f.Mh[i * n + j] + f.Mh[(k - i) * n + (k - j)]);
+              all[k].Kh[i * n + j] = 0.5 * (f.Kh[i * n + j] + f.Kh[(k - i) * n + (k - j)]);
+            }
         for (int i = 0; i < (2 * k + 1) * n; ++i)
           all[k].P[i] = f.P[i];
         for (int i = 0; i < (k + 2) * n; ++i)
@@ -54,6 +60,7 @@ namespace spirk
           all[k].xe[i] = f.xe[i], all[k].we[i] = f.we[i];
         for (int i = 0; i < n; ++i)
           all[k].nodes[i] = f.nodes[i];
+        all[k].Mv = all[k].Mh[k * n + k] + all[k].Mh[0], all[k].Kv = all[k].Kh[k * n + k] + all[k].Kh[0];
       }
     SPIRK_CUDA(cudaMemcpyToSymbol(c_fe, all, sizeof(all)));
     return SPIRK_OK;
@@ -391,6 +398,22 @@ int spirk_free_host(spirk_ctx *, double *ptr)
 long long spirk_level_n_dofs(const spirk_level *lvl) { return make_geo(lvl).N; }
 
 // ------------------------------------------------------------------------------- operator
+// fast-path dispatch: variant 0 (default) = plane-streaming kernel (op_v3.cuh), 2 / 3 = pipelined
+// tile-column kernel (op_v2.cuh), 1 = general cell kernel only (op_v1.cuh)
+static int fast_apply(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, V2Mode mode, double *dst, const double *src,
+                      const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
+                      const double *f2)
+{
+  if (ctx->opt_apply_variant == 1)
+    return SPIRK_ERR_UNSUPPORTED;
+  if (ctx->opt_apply_variant == 0)
+    {
+      int st = v3_apply(ctx, g, op, mode, dst, src, x_old, rhs, dinv, stride, f1, f2);
+      if (st != SPIRK_ERR_UNSUPPORTED)
+        return st;
+    }
+  return v2_apply(ctx, g, op, mode, dst, src, x_old, rhs, dinv, stride, f1, f2);
+}
 int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst, const double *src,
                    long long stride)
 {
@@ -401,12 +424,11 @@ int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *o
   if (dst == src)
     return set_error(SPIRK_ERR_INVALID, "op_apply: dst must not alias src");
   const Geo g = make_geo(lvl);
-  if (ctx->opt_apply_variant != 1)
-    {
-      int st = v2_apply(ctx, g, op, V2_APPLY, dst, src, nullptr, nullptr, nullptr, stride, nullptr, nullptr);
-      if (st != SPIRK_ERR_UNSUPPORTED)
-        return st;
-    }
+  {
+    int st = fast_apply(ctx, g, op, V2_APPLY, dst, src, nullptr, nullptr, nullptr, stride, nullptr, nullptr);
+    if (st != SPIRK_ERR_UNSUPPORTED)
+      return st;
+  }
   return apply_any(ctx, g, op, dst, src, stride);
 }
 
@@ -420,12 +442,11 @@ int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc
   if (dst == src)
     return set_error(SPIRK_ERR_INVALID, "op_residual: dst must not alias src");
   const Geo g = make_geo(lvl);
-  if (ctx->opt_apply_variant != 1)
-    {
-      int st = v2_apply(ctx, g, op, V2_RESIDUAL, dst, src, nullptr, rhs, nullptr, stride, nullptr, nullptr);
-      if (st != SPIRK_ERR_UNSUPPORTED)
-        return st;
-    }
+  {
+    int st = fast_apply(ctx, g, op, V2_RESIDUAL, dst, src, nullptr, rhs, nullptr, stride, nullptr, nullptr);
+    if (st != SPIRK_ERR_UNSUPPORTED)
+      return st;
+  }
   if (int e = ensure_scratch(ctx, (size_t)g.N * op->nb))
     return e;
   if (int e = apply_any(ctx, g, op, ctx->d_scratch, src, g.N))
@@ -446,12 +467,11 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
   if (x_new == x)
     return set_error(SPIRK_ERR_INVALID, "op_cheb_step: x_new must not alias x (it may alias x_old)");
   const Geo g = make_geo(lvl);
-  if (ctx->opt_apply_variant != 1)
-    {
-      int st = v2_apply(ctx, g, op, V2_CHEB, x_new, x, x_old, rhs, dinv, stride, f1, f2);
-      if (st != SPIRK_ERR_UNSUPPORTED)
-        return st;
-    }
+  {
+    int st = fast_apply(ctx, g, op, V2_CHEB, x_new, x, x_old, rhs, dinv, stride, f1, f2);
+    if (st != SPIRK_ERR_UNSUPPORTED)
+      return st;
+  }
   // general path: A x into scratch, then the pointwise update; dinv == NULL -> the operator's own
   // inverse diagonal (REAL operators only), materialised behind A x in the scratch buffer
   const bool own_dinv = (dinv == nullptr);

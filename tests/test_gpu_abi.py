@@ -33,28 +33,53 @@ def test_diag_transfer_problem(gpu_dev, dim, k, r):
     ac.check_problem(gpu_dev, dim, k, r)
 
 
-@pytest.mark.parametrize("r", [3, 4, 5])
-def test_fast_path_matches_general_kernel(gpu_dev, r):
-    """variant 2 (fused, tile columns) against variant 1 (general cell kernel) and the oracle"""
+@pytest.mark.parametrize("r,nb", [(3, 2), (4, 1), (5, 2), (4, 3)])
+def test_fast_path_matches_general_kernel(gpu_dev, r, nb):
+    """variant 0 (plane streaming, op_v3) and variant 2 (pipelined tile columns, op_v2) against
+    variant 1 (general cell kernel) and the oracle"""
     import ctypes as C
     import numpy as np
     from dealii_spirk_b200 import capi
     lvl, olv = ac.make_level(3, 4, r)
-    u = ac.block_input(olv, 2, seed=11)
-    op = capi.real_op([16.0, 2.9418686642961562], [0.1])
-    outs = []
+    u = ac.block_input(olv, nb, seed=11)
+    mass = [16.0, 2.9418686642961562, 5.644106850167844][:nb]
+    op = capi.real_op(mass, [0.1])
+    outs = {}
     with capi.Context(gpu_dev) as ctx:
         src, dst = ctx.upload(u), ctx.alloc(u.size)
-        for variant in (1, 0):
+        for variant in (1, 2, 0):
             ctx.call("spirk_ctx_set_option", b"apply_variant", variant)
             ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, olv.N)
-            outs.append(ctx.download(dst, u.shape))
-        ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, olv.N)
-        again = ctx.download(dst, u.shape)
+            outs[variant] = ctx.download(dst, u.shape)
+            if variant != 1:
+                ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, olv.N)
+                again = ctx.download(dst, u.shape)
+                assert np.array_equal(outs[variant], again), "fast paths must be bitwise reproducible (no atomics)"
+    assert ac.relerr(outs[2], outs[1]) < 1e-13
     assert ac.relerr(outs[0], outs[1]) < 1e-13
-    assert np.array_equal(outs[1], again), "variant 2 must be bitwise reproducible (no atomics)"
     if r <= 4:
-        assert ac.relerr(outs[1], olv.apply(u, [16.0, 2.9418686642961562], [0.1, 0.1])) < 1e-12
+        assert ac.relerr(outs[0], olv.apply(u, mass, [0.1] * nb)) < 1e-12
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+@pytest.mark.parametrize("r,nb", [(3, 1), (4, 2)])
+def test_fast_path_fused_epilogues(gpu_dev, variant, r, nb):
+    """residual / Chebyshev step (explicit and on-the-fly inverse diagonal, aliasing) on both fast paths"""
+    from dealii_spirk_b200 import capi
+
+    # set the variant option on every context the check opens
+    orig = capi.Context.__enter__
+
+    def enter(self):
+        ctx = orig(self)
+        ctx.call("spirk_ctx_set_option", b"apply_variant", variant)
+        return ctx
+
+    capi.Context.__enter__ = enter
+    try:
+        ac.check_residual_and_cheb(gpu_dev, 3, 4, r, nb)
+    finally:
+        capi.Context.__enter__ = orig
 
 
 def test_assemble_dense(gpu_dev):
