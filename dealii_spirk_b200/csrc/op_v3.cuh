@@ -38,6 +38,8 @@
 //   operator.h:298-310, 379-421 (vmult), 841-880 (batched); deal.II PreconditionChebyshev
 //   vector_updates and the residual of Multigrid::level_v_step (A8).
 #pragma once
+#include <cuda.h>
+
 #include <cstdint>
 
 #include "op_v2.cuh"
@@ -50,21 +52,23 @@ namespace spirk
   struct CfgV3
   {
     static constexpr int n = K + 1, OX = K * TX, OY = K * TY, LXS = OX + K + 1, LYS = OY + K + 1;
-    static constexpr int PUP  = (LXS + 2) & ~1; // staged row incl. the parity shift, whole 16-byte chunks
-    static constexpr int POP  = OX + 2;         // operand row incl. the parity shift
+    static constexpr int BW   = (LXS + 2) & ~1; // staged box: LXS nodes from a 16-byte aligned start, whole 16-byte chunks ...
+    static constexpr int BH   = (LYS + 1) / 2;  // ... x every other row (even / odd rows are separate boxes, see v3_make_map)
+    static constexpr int UB   = ((BW * BH + 15) / 16) * 16; // one box, padded to 128 bytes
+    static constexpr int OW   = OX + 2;         // operand box: the owned nodes (+ alignment slack) of every other row
+    static constexpr int OB   = OW * (OY / 2);
     static constexpr int PA   = OX | 1;         // odd pitch: lanes along y hit distinct banks
     static constexpr int NOPS = v3_nops(MODE);  // operand planes that travel with the staged plane
     static constexpr int NBUF = 3;              // ring depth (two planes in flight)
     static constexpr int NAC  = (NOPS == 2) ? 1 : 2; // a'/c tile double-buffered where shared memory allows
-    static constexpr int SLOT = LYS * PUP + NOPS * OY * POP;
+    static constexpr int SLOT = 2 * UB + NOPS * 2 * OB;
     static constexpr int NT   = OX * TY; // threads = y+z tasks
     static constexpr int NXT  = LYS * TX; // x-phase tasks
-    static constexpr int NROWS = LYS + NOPS * OY; // bulk copies per plane
     static constexpr int MINB = (NT >= 256) ? 2 : (NT >= 128 ? 4 : 8);
-    static constexpr unsigned ROWB_U = PUP * 8, ROWB_O = POP * 8;
-    static constexpr size_t   smem = sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
-    static_assert(NT % 32 == 0 && NT <= 1024 && NROWS <= NT, "tile shape");
-    static_assert(PUP % 2 == 0 && POP % 2 == 0 && SLOT % 2 == 0 && (LYS * PUP) % 2 == 0, "16-byte aligned rows");
+    static constexpr unsigned BYTES_U = 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
+    static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
+    static_assert(NT % 32 == 0 && NT <= 1024, "tile shape");
+    static_assert(UB % 16 == 0 && OB % 16 == 0 && OY % 2 == 0 && BW <= 256 && BH <= 256, "128-byte aligned TMA boxes");
   };
 
   // Mh / Kh are symmetric and persymmetric (made exact at upload): index the canonical copy of an entry so
@@ -89,6 +93,9 @@ namespace spirk
     double        cm[SPIRK_MAX_BLOCKS], cl[SPIRK_MAX_BLOCKS], f1[SPIRK_MAX_BLOCKS], f2[SPIRK_MAX_BLOCKS];
     int           ntx, nty;
     long long     W; // nb * columns * layers
+    long long     rows_per_block; // stride / n1: the blocks continue the row sequence of block 0
+    int           sh_src, sh_o0, sh_o1; // element shift of the 16-byte aligned map base below the vector
+    alignas(64) CUtensorMap tm_src, tm_o0, tm_o1; // staged nodes; operand 0 (rhs | x_old); operand 1 (rhs)
   };
 
   __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -109,11 +116,13 @@ namespace spirk
                  : "memory");
     return ok != 0;
   }
-  // bulk-async (TMA) 1-D copy global -> shared, completion counted in bytes on an mbarrier
-  __device__ __forceinline__ void bulk_g2s(const unsigned dst, const void *src, const unsigned bytes, const unsigned bar)
+  // TMA 2-D tile copy global -> shared (box of the tensor map at element coordinates c0, c1), completion
+  // counted in bytes on an mbarrier; out-of-bounds elements are zero-filled
+  __device__ __forceinline__ void tma_g2s_2d(const unsigned dst, const CUtensorMap *map, const int c0, const int c1,
+                                             const unsigned bar)
   {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(bar)
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
                  : "memory");
   }
 
@@ -135,12 +144,13 @@ namespace spirk
   }
 
   template <int K, int TX, int TY, int MODE>
-  __global__ void __launch_bounds__(CfgV3<K, TX, TY, MODE>::NT, CfgV3<K, TX, TY, MODE>::MINB) k_v3(const V3Args a)
+  __global__ void __launch_bounds__(CfgV3<K, TX, TY, MODE>::NT, CfgV3<K, TX, TY, MODE>::MINB) k_v3(const __grid_constant__ V3Args a)
   {
     using C = CfgV3<K, TX, TY, MODE>;
-    constexpr int n = C::n, OX = C::OX, OY = C::OY, LYS = C::LYS, PUP = C::PUP, POP = C::POP, PA = C::PA, NT = C::NT;
+    constexpr int n = C::n, OX = C::OX, OY = C::OY, LYS = C::LYS, BW = C::BW, UB = C::UB, OW = C::OW, OB = C::OB, PA = C::PA, NT = C::NT;
     constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT;
-    extern __shared__ __align__(16) double sm3[];
+    extern __shared__ __align__(16) double sm3_raw[];
+    double   *sm3  = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sm3_raw) + 127) & ~(uintptr_t)127); // TMA boxes: 128 bytes
     double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K;
     uint64_t *BAR  = reinterpret_cast<uint64_t *>(SDI + K * K * K);
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
@@ -202,52 +212,57 @@ namespace spirk
             b_tab = b;
           }
 
-        // ------------------------------------------------------------------ this thread's bulk copy of a plane
-        // tid < LYS: staged row tid of src; then OY rows of operand 0 (x_old | rhs), then OY rows of operand 1 (rhs)
-        const double *my_base  = nullptr;
-        unsigned      my_soff  = 0, my_bytes = 0;
-        bool          my_is_op = false;
-        int           nvalid_u = 0; // staged rows inside the domain and off the Dirichlet boundary
-        {
-          for (int r = 0; r < LYS; ++r)
-            {
-              const int gy = gy0 - K + r;
-              nvalid_u += (gy > 0 && gy < n1 - 1) ? 1 : 0;
-            }
-          if (tid < LYS)
-            {
-              const int gy = gy0 - K + tid;
-              if (gy > 0 && gy < n1 - 1)
-                my_base = src + (gx0 - K) + (long long)n1 * gy;
-              my_soff = tid * PUP * 8, my_bytes = C::ROWB_U;
-            }
-          else if (NOPS > 0 && tid < C::NROWS)
-            {
-              const int     o  = (tid - LYS) / OY, ro = (tid - LYS) % OY;
-              const double *ob = (MODE == V2_RESIDUAL) ? a.rhs : (o == 0 ? a.x_old : a.rhs);
-              if (ob != nullptr)
-                my_base = ob + boff + gx0 + (long long)n1 * (gy0 + ro);
-              my_soff = (LYS * PUP + (o * OY + ro) * POP) * 8, my_bytes = C::ROWB_O, my_is_op = true;
-            }
-        }
-        const unsigned op_bytes = (MODE == V2_RESIDUAL) ? OY * C::ROWB_O : (NOPS == 2 ? (has_xo ? 2 : 1) * OY * C::ROWB_O : 0);
-        auto           issue    = [&](const int sidx) {
-          const int      P     = K * zf + sidx;
-          const unsigned slot  = (it0 + sidx) % NBUF;
-          const bool     zpl   = (P <= 0) || (P >= n1 - 1);
-          const bool     owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+        // ------------------------------------------------------------------ staging of one node plane (one thread)
+        // Rows of all planes and blocks form ONE sequence of pitch n1 (row index R = y + n1 (z + n1 b)); the tensor
+        // maps view pairs of rows as super-rows of pitch 2 n1 (a multiple of 16 bytes although n1 is odd), so the
+        // even and the odd rows of a staged plane are one 2-D box each.
+        const long long Rb0 = (long long)b * a.rows_per_block + (long long)n1 * (K * zf) + (gy0 - K); // staged row 0 of step 0
+        const bool      has_o0 = (MODE == V2_RESIDUAL) || (MODE == V2_CHEB_OWN && has_xo);
+        auto            issue  = [&](const int sidx) {
           if (tid == 0)
-            mbar_arrive_expect_tx(bar_u32 + 8 * slot, (zpl ? 0u : nvalid_u * C::ROWB_U) + (owned ? op_bytes : 0u));
-          if (my_base != nullptr && (my_is_op ? owned : !zpl))
             {
-              const uintptr_t p = reinterpret_cast<uintptr_t>(my_base + plane * P) & ~(uintptr_t)15;
-              bulk_g2s(ring_u32 + slot * (SLOT * 8) + my_soff, reinterpret_cast<const void *>(p), my_bytes, bar_u32 + 8 * slot);
+              const int       P     = K * zf + sidx;
+              const unsigned  slot  = (it0 + sidx) % NBUF;
+              const bool      zpl   = (P <= 0) || (P >= n1 - 1);
+              const bool      owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+              const unsigned  bar   = bar_u32 + 8 * slot, dst = ring_u32 + slot * (SLOT * 8);
+              const long long Rb    = Rb0 + (long long)n1 * sidx, Ro = Rb + K;
+              mbar_arrive_expect_tx(bar, (zpl ? 0u : C::BYTES_U) + (owned ? ((has_o0 ? 1u : 0u) + (NOPS == 2 ? 1u : 0u)) * C::BYTES_O : 0u));
+              if (!zpl)
+                {
+                  tma_g2s_2d(dst, &a.tm_src, (gx0 - K + a.sh_src) & ~1, (int)((Rb + 1) >> 1), bar);
+                  tma_g2s_2d(dst + UB * 8, &a.tm_src, (n1 + gx0 - K + a.sh_src) & ~1, (int)(Rb >> 1), bar);
+                }
+              if (owned)
+                {
+                  if (has_o0)
+                    {
+                      tma_g2s_2d(dst + 2 * UB * 8, &a.tm_o0, (gx0 + a.sh_o0) & ~1, (int)((Ro + 1) >> 1), bar);
+                      tma_g2s_2d(dst + (2 * UB + OB) * 8, &a.tm_o0, (n1 + gx0 + a.sh_o0) & ~1, (int)(Ro >> 1), bar);
+                    }
+                  if (NOPS == 2)
+                    {
+                      tma_g2s_2d(dst + (2 * UB + 2 * OB) * 8, &a.tm_o1, (gx0 + a.sh_o1) & ~1, (int)((Ro + 1) >> 1), bar);
+                      tma_g2s_2d(dst + (2 * UB + 3 * OB) * 8, &a.tm_o1, (n1 + gx0 + a.sh_o1) & ~1, (int)(Ro >> 1), bar);
+                    }
+                }
             }
         };
-        // parities (n1 is odd: a row / plane step flips the 8-byte parity of the row start)
-        const int par_u  = (int)((reinterpret_cast<uintptr_t>(src) >> 3) & 1) + gx0 - K + gy0 - K + K * zf;
-        const int par_o0 = (NOPS > 0) ? (int)((reinterpret_cast<uintptr_t>((MODE == V2_RESIDUAL ? a.rhs : a.x_old) + boff) >> 3) & 1) + gx0 + gy0 + K * zf : 0;
-        const int par_o1 = (NOPS > 1) ? (int)((reinterpret_cast<uintptr_t>(a.rhs + boff) >> 3) & 1) + gx0 + gy0 + K * zf : 0;
+        // shared-memory offset of staged row r (0..LYS-1) / operand row ro (0..OY-1) of the plane of step s_:
+        // box of the row's parity, position inside the box, and the 8-byte parity of the row start (a box starts
+        // at the 16-byte aligned element at or below the first wanted one; gx0, K even, n1 odd)
+        const int rb0_par = (int)(Rb0 & 1);
+        auto      urow    = [&](const int r, const int s_) {
+          const int par = (rb0_par + s_) & 1; // parity of the staged row 0 of this step (n1 is odd)
+          const int blk = (par + r) & 1;
+          // rows of parity `blk`: r = (par ^ blk), +2, ...: index (r - (par ^ blk)) / 2
+          return blk * UB + ((r - (par ^ blk)) >> 1) * BW + (a.sh_src ^ blk);
+        };
+        auto orow = [&](const int ro, const int s_, const int sh) {
+          const int par = (rb0_par + s_) & 1; // K is even: operand row 0 (= staged row K) has the same parity
+          const int blk = (par + ro) & 1;
+          return blk * OB + ((ro - (par ^ blk)) >> 1) * OW + (sh ^ blk);
+        };
 
         double acc[n][K]; // z-sums of the current layer: planes 0..K x the K owned nodes of this thread
 #pragma unroll
@@ -284,7 +299,7 @@ namespace spirk
                   }
                 else
                   {
-                    const double *ur = ub + row * PUP + ((par_u + row + s) & 1) + K * seg;
+                    const double *ur = ub + urow(row, s) + K * seg;
                     double        u[2 * K + 1];
 #pragma unroll
                     for (int j = 0; j < 2 * K + 1; ++j)
@@ -374,19 +389,17 @@ namespace spirk
                   {
 #pragma unroll
                     for (int i = 0; i < K; ++i)
-                      g[i] = ub[LYS * PUP + (K * ys + i) * POP + xl + ((par_o0 + K * ys + i + s) & 1)];
+                      g[i] = ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl];
                   }
                 else
                   {
-                    const double *o1  = ub + LYS * PUP + (OY + K * ys) * POP + xl;
-                    const double *ux  = ub + (K + K * ys) * PUP + K + xl;
                     const double *sdi = SDI + ((P % K) * K) * K + (xl % K);
 #pragma unroll
                     for (int i = 0; i < K; ++i)
                       {
-                        const double x   = ux[i * PUP + ((par_u + K + K * ys + i + s) & 1)];
-                        const double xo  = has_xo ? ub[LYS * PUP + (K * ys + i) * POP + xl + ((par_o0 + K * ys + i + s) & 1)] : 0.0;
-                        const double rh  = o1[i * POP + ((par_o1 + K * ys + i + s) & 1)];
+                        const double x  = ub[urow(K + K * ys + i, s) + K + xl];
+                        const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl] : 0.0;
+                        const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, s, a.sh_o1) + xl];
                         g[i]             = fma(fma(f1, x - xo, x), sdi[i * K], rh);
                       }
                   }
@@ -510,8 +523,46 @@ namespace spirk
 #undef KC
   }
 
+  // ---------------------------------------------------------------------------------------------------------
+  // Tensor map over a block vector of `n_elems` doubles starting at `ptr` (8-byte aligned): 2-D view
+  // [n_elems' / (2 n1)] x [2 n1] ("super-rows" = pairs of node rows) based at the 16-byte aligned address at or
+  // below ptr; *shift = elements between that base and ptr (0 or 1, to be added to x coordinates).
+  typedef CUresult (*PFN_tmap_encode_tiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                            const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  inline PFN_tmap_encode_tiled v3_encode_fn()
+  {
+    static PFN_tmap_encode_tiled fn = nullptr;
+    if (!fn)
+      {
+        void                           *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+          fn = reinterpret_cast<PFN_tmap_encode_tiled>(p);
+      }
+    return fn;
+  }
+  inline int v3_make_map(CUtensorMap *map, int *shift, const double *ptr, const long long n_elems, const int n1, const int box_w,
+                         const int box_h)
+  {
+    PFN_tmap_encode_tiled enc = v3_encode_fn();
+    if (!enc)
+      return set_error(SPIRK_ERR_DEVICE, "cuTensorMapEncodeTiled is not available");
+    const uintptr_t  p0 = reinterpret_cast<uintptr_t>(ptr);
+    *shift              = (int)((p0 >> 3) & 1);
+    void            *base = reinterpret_cast<void *>(p0 & ~(uintptr_t)15);
+    const cuuint64_t dims[2]    = {(cuuint64_t)2 * n1, (cuuint64_t)((n_elems + *shift) / (2LL * n1))};
+    const cuuint64_t strides[1] = {(cuuint64_t)2 * n1 * sizeof(double)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
+    const CUresult   r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return set_error(SPIRK_ERR_DEVICE, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return SPIRK_OK;
+  }
+
   template <int K, int TX, int TY, int MODE>
-  int v3_launch_mode(spirk_ctx *ctx, const V3Args &a)
+  int v3_launch_mode(spirk_ctx *ctx, V3Args &a)
   {
     using C = CfgV3<K, TX, TY, MODE>;
     static bool attr_set = false;
@@ -520,6 +571,17 @@ namespace spirk
         SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
         attr_set = true;
       }
+    const long long n_elems = (long long)(a.nb - 1) * a.stride + a.g.N;
+    if (int e = v3_make_map(&a.tm_src, &a.sh_src, a.src, n_elems, a.g.n1, C::BW, C::BH))
+      return e;
+    a.tm_o0 = a.tm_src, a.tm_o1 = a.tm_src, a.sh_o0 = a.sh_o1 = 0;
+    const double *o0 = (MODE == V2_RESIDUAL) ? a.rhs : (MODE == V2_CHEB_OWN ? a.x_old : nullptr);
+    if (o0 != nullptr)
+      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, o0, n_elems, a.g.n1, C::OW, C::OY / 2))
+        return e;
+    if (MODE == V2_CHEB_OWN)
+      if (int e = v3_make_map(&a.tm_o1, &a.sh_o1, a.rhs, n_elems, a.g.n1, C::OW, C::OY / 2))
+        return e;
     // fixed grid: all co-resident CTAs, but no piece shorter than ~4 layers (a piece above layer 0
     // recomputes one layer)
     const long long slots = (long long)ctx->n_sms * C::MINB;
@@ -550,8 +612,10 @@ namespace spirk
   {
     if (g.dim != 3 || g.k != 4 || op->kind != SPIRK_OP_REAL || g.nc % 8 != 0 || g.nc < 8)
       return SPIRK_ERR_UNSUPPORTED;
+    if (op->nb > 1 && stride % g.n1 != 0)
+      return SPIRK_ERR_UNSUPPORTED; // the blocks must continue the row sequence of block 0 (one tensor map)
     V3Args a;
-    a.g = g, a.nb = op->nb, a.stride = stride;
+    a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1;
     a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = dinv;
     const double hd = g.h * g.h * g.h, hl = g.h;
     for (int b = 0; b < op->nb; ++b)
