@@ -59,15 +59,18 @@ namespace spirk
     static constexpr int OB   = OW * (OY / 2);
     static constexpr int PA   = OX | 1;         // odd pitch: lanes along y hit distinct banks
     static constexpr int NOPS = v3_nops(MODE);  // operand planes that travel with the staged plane
-    static constexpr int NBUF = 3;              // ring depth (two planes in flight)
+    static constexpr int NBUF = (NOPS == 0) ? 4 : 3; // ring depth (three / two planes in flight; 2 CTAs per SM must fit)
     static constexpr int NAC  = (NOPS == 2) ? 1 : 2; // a'/c tile double-buffered where shared memory allows
     static constexpr int SLOT = 2 * UB + NOPS * 2 * OB;
-    static constexpr int NT   = OX * TY; // threads = y+z tasks
+    static constexpr int NY   = OX * TY;  // y+z tasks (one thread each)
     static constexpr int NXT  = LYS * TX; // x-phase tasks
-    static constexpr int MINB = (NT >= 256) ? 2 : (NT >= 128 ? 4 : 8);
+    static constexpr int NT   = ((NXT > NY ? NXT : NY) + 31) / 32 * 32; // one x task per thread; the threads beyond NY are helpers:
+                                                                         // TMA issue, Dirichlet faces
+    static constexpr int NH   = NT - NY;
+    static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 4 : 8);
     static constexpr unsigned BYTES_U = 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
     static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
-    static_assert(NT % 32 == 0 && NT <= 1024, "tile shape");
+    static_assert(NY % 32 == 0 && NT <= 1024 && NH >= 32, "tile shape");
     static_assert(UB % 16 == 0 && OB % 16 == 0 && OY % 2 == 0 && BW <= 256 && BH <= 256, "128-byte aligned TMA boxes");
   };
 
@@ -93,6 +96,7 @@ namespace spirk
     double        cm[SPIRK_MAX_BLOCKS], cl[SPIRK_MAX_BLOCKS], f1[SPIRK_MAX_BLOCKS], f2[SPIRK_MAX_BLOCKS];
     int           ntx, nty;
     long long     W; // nb * columns * layers
+    int           lock_nch, lock_len; // > 0: z-lockstep schedule (CTA = one column x one of lock_nch equal layer ranges)
     long long     rows_per_block; // stride / n1: the blocks continue the row sequence of block 0
     int           sh_src, sh_o0, sh_o1; // element shift of the 16-byte aligned map base below the vector
     alignas(64) CUtensorMap tm_src, tm_o0, tm_o1; // staged nodes; operand 0 (rhs | x_old); operand 1 (rhs)
@@ -148,9 +152,9 @@ namespace spirk
   {
     using C = CfgV3<K, TX, TY, MODE>;
     constexpr int n = C::n, OX = C::OX, OY = C::OY, LYS = C::LYS, BW = C::BW, UB = C::UB, OW = C::OW, OB = C::OB, PA = C::PA, NT = C::NT;
-    constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT;
+    constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT, NY = C::NY, NH = C::NH;
     extern __shared__ __align__(16) double sm3_raw[];
-    double   *sm3  = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(sm3_raw) + 127) & ~(uintptr_t)127); // TMA boxes: 128 bytes
+    double   *sm3  = sm3_raw + (((128u - (smem_u32(sm3_raw) & 127u)) & 127u) >> 3); // TMA boxes: 128-byte aligned
     double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K;
     uint64_t *BAR  = reinterpret_cast<uint64_t *>(SDI + K * K * K);
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
@@ -162,7 +166,8 @@ namespace spirk
     const int       n1 = a.g.n1, nc = a.g.nc;
     const long long plane = (long long)n1 * n1;
     const int       ncols = a.ntx * a.nty;
-    const int       xl = tid % OX, ys = tid / OX; // y+z task: owned x, cell segment in y
+    const bool      is_yz = tid < NY;                    // the other threads only take an x task, the TMA issue and the faces
+    const int       xl = tid % OX, ys = (tid / OX) % TY; // y+z task: owned x, cell segment in y
 
     if (tid == 0)
       {
@@ -174,8 +179,17 @@ namespace spirk
       }
     const unsigned ring_u32 = smem_u32(RING), bar_u32 = smem_u32(BAR);
 
-    long long       w     = a.W * blockIdx.x / gridDim.x;
-    const long long w_end = a.W * (blockIdx.x + 1) / gridDim.x;
+    // work range in the (block, column, layer) space: an even split of the whole space, or - for vectors beyond
+    // the L2 capacity - one column x one layer range per CTA with neighbouring CTAs on neighbouring columns at
+    // the same height, so that the halo rows / columns shared by adjacent tiles meet in L2
+    long long w = a.W * blockIdx.x / gridDim.x, w_end = a.W * (blockIdx.x + 1) / gridDim.x;
+    if (a.lock_nch > 0)
+      {
+        const long long colb = blockIdx.x % ((long long)ncols), rest = blockIdx.x / ncols;
+        const int       ch = (int)(rest % a.lock_nch), bb = (int)(rest / a.lock_nch);
+        w     = ((long long)bb * ncols + colb) * nc + min(nc, ch * a.lock_len);
+        w_end = ((long long)bb * ncols + colb) * nc + min(nc, (ch + 1) * a.lock_len);
+      }
     int             b_tab = -1;
     unsigned        it0   = 0; // ring position of the piece's first plane (runs on across pieces)
     while (w < w_end)
@@ -194,6 +208,7 @@ namespace spirk
         const int       zf   = (L0 > 0) ? L0 - 1 : 0;      // first layer that is processed (recomputed if < L0)
         const int       nsteps = 1 + K * (L1 - zf);        // node planes K zf .. K L1
         const bool      has_xo = (a.x_old != nullptr);
+        const bool      edge_x = (tx == 0) || (tx == a.ntx - 1);
 
         __syncthreads(); // the previous piece is finished with the ring, the a'/c tile and the tables
         if (MODE == V2_CHEB_OWN && b != b_tab)
@@ -219,7 +234,7 @@ namespace spirk
         const long long Rb0 = (long long)b * a.rows_per_block + (long long)n1 * (K * zf) + (gy0 - K); // staged row 0 of step 0
         const bool      has_o0 = (MODE == V2_RESIDUAL) || (MODE == V2_CHEB_OWN && has_xo);
         auto            issue  = [&](const int sidx) {
-          if (tid == 0)
+          if (tid == NY)
             {
               const int       P     = K * zf + sidx;
               const unsigned  slot  = (it0 + sidx) % NBUF;
@@ -304,24 +319,32 @@ namespace spirk
 #pragma unroll
                     for (int j = 0; j < 2 * K + 1; ++j)
                       u[j] = ur[j];
-                    if (seg == 0 && tx == 0)
-                      { // x < 0 (outside) and x = 0 (Dirichlet)
+                    if (edge_x)
+                      {
+                        if (seg == 0 && tx == 0)
+                          { // x < 0 (outside) and x = 0 (Dirichlet)
 #pragma unroll
-                        for (int j = 0; j <= K; ++j)
-                          u[j] = 0.0;
+                            for (int j = 0; j <= K; ++j)
+                              u[j] = 0.0;
+                          }
+                        if (seg == 1 && tx == 0)
+                          u[0] = 0.0; // x = 0 seen from the second cell
+                        if (seg == TX - 1 && tx == a.ntx - 1)
+                          u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
                       }
-                    if (seg == 1 && tx == 0)
-                      u[0] = 0.0; // x = 0 seen from the second cell
-                    if (seg == TX - 1 && tx == a.ntx - 1)
-                      u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
+                    // vertex row: two partial sums each (short dependency chains)
                     double am[K], ak[K];
-                    am[0] = Mv * u[K], ak[0] = Kv * u[K];
+                    {
+                      double m1 = MC(0, 1) * u[K + 1], k1 = KC(0, 1) * u[K + 1];
+                      am[0] = Mv * u[K], ak[0] = Kv * u[K];
 #pragma unroll
-                    for (int j = 0; j < K; ++j)
-                      am[0] = fma(MC(K, j), u[j], am[0]), ak[0] = fma(KC(K, j), u[j], ak[0]);
+                      for (int j = 0; j < K; ++j)
+                        am[0] = fma(MC(K, j), u[j], am[0]), ak[0] = fma(KC(K, j), u[j], ak[0]);
 #pragma unroll
-                    for (int j = 1; j <= K; ++j)
-                      am[0] = fma(MC(0, j), u[K + j], am[0]), ak[0] = fma(KC(0, j), u[K + j], ak[0]);
+                      for (int j = 2; j <= K; ++j)
+                        m1 = fma(MC(0, j), u[K + j], m1), k1 = fma(KC(0, j), u[K + j], k1);
+                      am[0] += m1, ak[0] += k1;
+                    }
 #pragma unroll
                     for (int i = 1; i < K; ++i)
                       {
@@ -340,174 +363,187 @@ namespace spirk
             if (s >= 1 && s - 1 + NBUF < nsteps)
               issue(s - 1 + NBUF);
 
-            // -------------------------------------------------------------- y-sweep
-            double p[K], wv[K];
-            {
-              const double *ar = SA + (K * ys) * PA + xl, *cr = SC + (K * ys) * PA + xl;
-              double        av[2 * K + 1], cv[2 * K + 1];
-#pragma unroll
-              for (int j = 0; j < 2 * K + 1; ++j)
-                av[j] = ar[j * PA], cv[j] = cr[j * PA];
-              p[0]  = Mv * av[K];
-              wv[0] = fma(Kv, av[K], Mv * cv[K]);
-#pragma unroll
-              for (int j = 0; j < K; ++j)
-                {
-                  p[0]  = fma(MC(K, j), av[j], p[0]);
-                  wv[0] = fma(MC(K, j), cv[j], fma(KC(K, j), av[j], wv[0]));
-                }
-#pragma unroll
-              for (int j = 1; j <= K; ++j)
-                {
-                  p[0]  = fma(MC(0, j), av[K + j], p[0]);
-                  wv[0] = fma(MC(0, j), cv[K + j], fma(KC(0, j), av[K + j], wv[0]));
-                }
-#pragma unroll
-              for (int i = 1; i < K; ++i)
-                {
-                  p[i]  = MC(i, 0) * av[K];
-                  wv[i] = fma(KC(i, 0), av[K], MC(i, 0) * cv[K]);
-#pragma unroll
-                  for (int j = 1; j <= K; ++j)
-                    {
-                      p[i]  = fma(MC(i, j), av[K + j], p[i]);
-                      wv[i] = fma(MC(i, j), cv[K + j], fma(KC(i, j), av[K + j], wv[i]));
-                    }
-                }
-            }
-            // -------------------------------------------------------------- linear part of the epilogue of this plane
-            // g = rhs (residual) | rhs + ((1 + f1) x - f1 x_old) / (f2 dinv) (Chebyshev); the z-sums run on A x - g
-            const int  zl    = (s == 0) ? 0 : ((s - 1) % K) + 1;
-            const bool owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
-            double     g[K];
-#pragma unroll
-            for (int i = 0; i < K; ++i)
-              g[i] = 0.0;
-            if (NOPS > 0 && owned)
+            if (is_yz)
               {
-                if (MODE == V2_RESIDUAL)
+              // -------------------------------------------------------------- y-sweep
+              double p[K], wv[K];
+              {
+                const double *ar = SA + (K * ys) * PA + xl, *cr = SC + (K * ys) * PA + xl;
+                double        av[2 * K + 1], cv[2 * K + 1];
+  #pragma unroll
+                for (int j = 0; j < 2 * K + 1; ++j)
+                  av[j] = ar[j * PA], cv[j] = cr[j * PA];
+                // vertex row: four partial sums for w, two for p'; interior rows: M c and K a' separately
+                {
+                  double p1 = MC(0, 1) * av[K + 1], wm1 = MC(0, 1) * cv[K + 1], wk0 = Kv * av[K], wk1 = KC(0, 1) * av[K + 1];
+                  p[0] = Mv * av[K], wv[0] = Mv * cv[K];
+  #pragma unroll
+                  for (int j = 0; j < K; ++j)
+                    {
+                      p[0]  = fma(MC(K, j), av[j], p[0]);
+                      wv[0] = fma(MC(K, j), cv[j], wv[0]);
+                      wk0   = fma(KC(K, j), av[j], wk0);
+                    }
+  #pragma unroll
+                  for (int j = 2; j <= K; ++j)
+                    {
+                      p1  = fma(MC(0, j), av[K + j], p1);
+                      wm1 = fma(MC(0, j), cv[K + j], wm1);
+                      wk1 = fma(KC(0, j), av[K + j], wk1);
+                    }
+                  p[0] += p1, wv[0] = (wv[0] + wm1) + (wk0 + wk1);
+                }
+  #pragma unroll
+                for (int i = 1; i < K; ++i)
                   {
-#pragma unroll
-                    for (int i = 0; i < K; ++i)
-                      g[i] = ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl];
-                  }
-                else
-                  {
-                    const double *sdi = SDI + ((P % K) * K) * K + (xl % K);
-#pragma unroll
-                    for (int i = 0; i < K; ++i)
+                    double wk = KC(i, 0) * av[K];
+                    p[i] = MC(i, 0) * av[K], wv[i] = MC(i, 0) * cv[K];
+  #pragma unroll
+                    for (int j = 1; j <= K; ++j)
                       {
-                        const double x  = ub[urow(K + K * ys + i, s) + K + xl];
-                        const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl] : 0.0;
-                        const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, s, a.sh_o1) + xl];
-                        g[i]             = fma(fma(f1, x - xo, x), sdi[i * K], rh);
+                        p[i]  = fma(MC(i, j), av[K + j], p[i]);
+                        wv[i] = fma(MC(i, j), cv[K + j], wv[i]);
+                        wk    = fma(KC(i, j), av[K + j], wk);
                       }
+                    wv[i] += wk;
                   }
               }
-            // -------------------------------------------------------------- z-accumulation
-            if (zl < K)
-              {
-                // columns 0..K-1 of the cell matrices (uniform switch keeps the entries in few registers)
-#pragma unroll
-                for (int zz = 0; zz < K; ++zz)
-                  if (zl == zz)
+              // -------------------------------------------------------------- linear part of the epilogue of this plane
+              // g = rhs (residual) | rhs + ((1 + f1) x - f1 x_old) / (f2 dinv) (Chebyshev); the z-sums run on A x - g
+              const int  zl    = (s == 0) ? 0 : ((s - 1) % K) + 1;
+              const bool owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+              double     g[K];
+  #pragma unroll
+              for (int i = 0; i < K; ++i)
+                g[i] = 0.0;
+              if (NOPS > 0 && owned)
+                {
+                  if (MODE == V2_RESIDUAL)
                     {
-#pragma unroll
-                      for (int z = 0; z < n; ++z)
-#pragma unroll
-                        for (int i = 0; i < K; ++i)
-                          acc[z][i] = fma(MC(z, zz), wv[i], fma(KC(z, zz), p[i], acc[z][i]));
-                      if (NOPS > 0 && zz > 0)
+  #pragma unroll
+                      for (int i = 0; i < K; ++i)
+                        g[i] = ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl];
+                    }
+                  else
+                    {
+                      const double *sdi = SDI + ((P % K) * K) * K + (xl % K);
+  #pragma unroll
+                      for (int i = 0; i < K; ++i)
                         {
-#pragma unroll
-                          for (int i = 0; i < K; ++i)
-                            acc[zz][i] -= g[i];
+                          const double x  = ub[urow(K + K * ys + i, s) + K + xl];
+                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl] : 0.0;
+                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, s, a.sh_o1) + xl];
+                          g[i]             = fma(fma(f1, x - xo, x), sdi[i * K], rh);
                         }
                     }
-              }
-            else
-              {
-                const int Lc = zf + (s - 1) / K; // the layer that this (top) plane completes
-#pragma unroll
-                for (int z = 0; z < n; ++z)
-#pragma unroll
-                  for (int i = 0; i < K; ++i)
-                    acc[z][i] = fma(MC(z, K), wv[i], fma(KC(z, K), p[i], acc[z][i]));
-                if (Lc >= L0)
-                  {
-                    const int       gx = gx0 + xl, gy = gy0 + K * ys;
-                    const long long j0 = boff + gx + (long long)n1 * gy + plane * (K * Lc);
-                    const bool      anyb = (gx == 0) || (gy == 0) || (Lc == 0);
-                    if (MODE == V2_CHEB)
+                }
+              // -------------------------------------------------------------- z-accumulation
+              if (zl < K)
+                {
+                  // columns 0..K-1 of the cell matrices (uniform switch keeps the entries in few registers)
+  #pragma unroll
+                  for (int zz = 0; zz < K; ++zz)
+                    if (zl == zz)
                       {
-                        // explicit inverse diagonal: operands straight from global memory
-#pragma unroll
-                        for (int z = 0; z < K; ++z)
-#pragma unroll
+  #pragma unroll
+                        for (int z = 0; z < n; ++z)
+  #pragma unroll
                           for (int i = 0; i < K; ++i)
+                            acc[z][i] = fma(MC(z, zz), wv[i], fma(KC(z, zz), p[i], acc[z][i]));
+                        if (NOPS > 0 && zz > 0)
+                          {
+  #pragma unroll
+                            for (int i = 0; i < K; ++i)
+                              acc[zz][i] -= g[i];
+                          }
+                      }
+                }
+              else
+                {
+                  const int Lc = zf + (s - 1) / K; // the layer that this (top) plane completes
+  #pragma unroll
+                  for (int z = 0; z < n; ++z)
+  #pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      acc[z][i] = fma(MC(z, K), wv[i], fma(KC(z, K), p[i], acc[z][i]));
+                  if (Lc >= L0)
+                    {
+                      const int       gx = gx0 + xl, gy = gy0 + K * ys;
+                      const long long j0 = boff + gx + (long long)n1 * gy + plane * (K * Lc);
+                      const bool      anyb = (gx == 0) || (gy == 0) || (Lc == 0);
+                      if (MODE == V2_CHEB)
+                        {
+                          // explicit inverse diagonal: operands straight from global memory
+  #pragma unroll
+                          for (int z = 0; z < K; ++z)
+  #pragma unroll
+                            for (int i = 0; i < K; ++i)
+                              {
+                                const long long j = j0 + z * plane + i * n1;
+                                if (anyb && ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0)))
+                                  v3_identity<MODE>(a, f1, f2, j);
+                                else
+                                  {
+                                    const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
+                                    a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - acc[z][i], fma(f1, x - xo, x));
+                                  }
+                              }
+                        }
+                      else
+                        {
+                          double       *dp  = a.dst + j0;
+                          const double *sds = SDS + (xl % K);
+                          if (!anyb)
                             {
-                              const long long j = j0 + z * plane + i * n1;
-                              if (anyb && ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0)))
-                                v3_identity<MODE>(a, f1, f2, j);
-                              else
-                                {
-                                  const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
-                                  a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - acc[z][i], fma(f1, x - xo, x));
-                                }
+  #pragma unroll
+                              for (int z = 0; z < K; ++z)
+  #pragma unroll
+                                for (int i = 0; i < K; ++i)
+                                  dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
+                                                           : (MODE == V2_RESIDUAL) ? -acc[z][i]
+                                                                                   : sds[(z * K + i) * K] * acc[z][i];
                             }
-                      }
-                    else
-                      {
-                        double       *dp  = a.dst + j0;
-                        const double *sds = SDS + (xl % K);
-                        if (!anyb)
-                          {
-#pragma unroll
-                            for (int z = 0; z < K; ++z)
-#pragma unroll
-                              for (int i = 0; i < K; ++i)
-                                dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
-                                                         : (MODE == V2_RESIDUAL) ? -acc[z][i]
-                                                                                 : sds[(z * K + i) * K] * acc[z][i];
-                          }
-                        else
-                          {
-#pragma unroll
-                            for (int z = 0; z < K; ++z)
-#pragma unroll
-                              for (int i = 0; i < K; ++i)
-                                {
-                                  if ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0))
-                                    v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1);
-                                  else
-                                    dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
-                                                             : (MODE == V2_RESIDUAL) ? -acc[z][i]
-                                                                                     : sds[(z * K + i) * K] * acc[z][i];
-                                }
-                          }
-                      }
-                    // Dirichlet faces x = n1-1 and y = n1-1 of these K planes (owned by no tile)
-                    if (tx == a.ntx - 1)
-                      {
-                        const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
-                        for (int e = tid; e < K * oye; e += NT)
-                          v3_identity<MODE>(a, f1, f2,
-                                            boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye));
-                      }
-                    if (ty == a.nty - 1)
-                      for (int e = tid; e < K * OX; e += NT)
-                        v3_identity<MODE>(a, f1, f2,
-                                          boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
-                  }
-                // the top plane becomes the bottom plane of the next layer
-#pragma unroll
-                for (int i = 0; i < K; ++i)
+                          else
+                            {
+  #pragma unroll
+                              for (int z = 0; z < K; ++z)
+  #pragma unroll
+                                for (int i = 0; i < K; ++i)
+                                  {
+                                    if ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0))
+                                      v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1);
+                                    else
+                                      dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
+                                                               : (MODE == V2_RESIDUAL) ? -acc[z][i]
+                                                                                       : sds[(z * K + i) * K] * acc[z][i];
+                                  }
+                            }
+                        }
+                    }
+                  // the top plane becomes the bottom plane of the next layer
+  #pragma unroll
+                  for (int i = 0; i < K; ++i)
+                    {
+                      acc[0][i] = fma(MC(0, 0), wv[i], fma(KC(0, 0), p[i], acc[K][i])) - g[i];
+  #pragma unroll
+                      for (int z = 1; z < n; ++z)
+                        acc[z][i] = fma(MC(z, 0), wv[i], KC(z, 0) * p[i]);
+                    }
+                }
+                        }
+            if (!is_yz && s > 0 && (s - 1) % K == K - 1 && zf + (s - 1) / K >= L0)
+              {
+                // helpers: Dirichlet faces x = n1-1 and y = n1-1 of the K planes of the completed layer (owned by no tile)
+                const int Lc = zf + (s - 1) / K, ht = tid - NY;
+                if (tx == a.ntx - 1)
                   {
-                    acc[0][i] = fma(MC(0, 0), wv[i], fma(KC(0, 0), p[i], acc[K][i])) - g[i];
-#pragma unroll
-                    for (int z = 1; z < n; ++z)
-                      acc[z][i] = fma(MC(z, 0), wv[i], KC(z, 0) * p[i]);
+                    const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
+                    for (int e = ht; e < K * oye; e += NH)
+                      v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye));
                   }
+                if (ty == a.nty - 1)
+                  for (int e = ht; e < K * OX; e += NH)
+                    v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
               }
           }
         it0 += nsteps;
@@ -542,6 +578,16 @@ namespace spirk
       }
     return fn;
   }
+  inline int v3_l2_promotion()
+  {
+    static int v = -1;
+    if (v < 0)
+      {
+        const char *e = getenv("SPIRK_V3_L2PROMO"); // tuning knob: 0 none, 1 64 B, 2 128 B, 3 256 B
+        v             = e ? atoi(e) : 0;
+      }
+    return v;
+  }
   inline int v3_make_map(CUtensorMap *map, int *shift, const double *ptr, const long long n_elems, const int n1, const int box_w,
                          const int box_h)
   {
@@ -555,7 +601,7 @@ namespace spirk
     const cuuint64_t strides[1] = {(cuuint64_t)2 * n1 * sizeof(double)};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
     const CUresult   r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)v3_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
       return set_error(SPIRK_ERR_DEVICE, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return SPIRK_OK;
@@ -585,7 +631,24 @@ namespace spirk
     // fixed grid: all co-resident CTAs, but no piece shorter than ~4 layers (a piece above layer 0
     // recomputes one layer)
     const long long slots = (long long)ctx->n_sms * C::MINB;
-    const long long grid  = std::max(1LL, std::min(slots, a.W / 4));
+    long long       grid  = std::max(1LL, std::min(slots, a.W / 4));
+    a.lock_nch = 0, a.lock_len = 0;
+    {
+      static int force = -2;
+      if (force == -2)
+        {
+          const char *e = getenv("SPIRK_V3_LOCKSTEP"); // tuning knob: 0 off, 1 on, unset: by vector size
+          force         = e ? atoi(e) : -1;
+        }
+      const long long cols = (long long)a.nb * a.ntx * a.nty;
+      const int       nch  = (int)std::max(1LL, std::min(slots / cols, (long long)a.g.nc / 8)); // ranges of >= 8 layers
+      if (force == 1 || (force == -1 && 2 * cols * nch >= slots))
+        {
+          a.lock_len = (a.g.nc + nch - 1) / nch;
+          a.lock_nch = (a.g.nc + a.lock_len - 1) / a.lock_len;
+          grid       = cols * a.lock_nch;
+        }
+    }
     k_v3<K, TX, TY, MODE><<<(unsigned int)grid, C::NT, C::smem, ctx->stream>>>(a);
     SPIRK_LAUNCH_CHECK(ctx);
     return SPIRK_OK;
