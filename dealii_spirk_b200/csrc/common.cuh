@@ -103,6 +103,8 @@ namespace spirk
   int ensure_scratch(spirk_ctx *ctx, size_t n);
   int ensure_tab(spirk_ctx *ctx, size_t n);
   int upload_fe_constants();
+  // host copy of the reference matrices as uploaded (exactly persymmetric), (k+1)^2 entries each
+  void fe_host_sym(int k, double *Mh, double *Kh);
   // reduce-to-host helper: sums ctx->d_partials[0..count) per result slot
   int finish_reduction(spirk_ctx *ctx, int n_results, int n_blocks, double *host_out);
 } // namespace spirk

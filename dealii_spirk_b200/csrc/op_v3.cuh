@@ -41,6 +41,7 @@
 #include <cuda.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "op_v2.cuh"
 
@@ -86,6 +87,24 @@ namespace spirk
     return a * (K + 1) + b;
   }
 
+  // position of the canonical copy of entry (i, j) in the compact list of distinct entries
+  template <int K>
+  __host__ __device__ constexpr int v3_cidx(const int i, const int j)
+  {
+    const int c   = v3_canon<K>(i, j);
+    int       cnt = 0;
+    for (int a = 0; a <= K; ++a)
+      for (int b = a; b <= K; ++b)
+        if (v3_canon<K>(a, b) == a * (K + 1) + b)
+          {
+            if (a * (K + 1) + b == c)
+              return cnt;
+            ++cnt;
+          }
+    return -1;
+  }
+  constexpr int V3_NKP = 20; // distinct entries of K' per block (16 at k = 6) + the vertex diagonal in the last slot
+
   struct V3Args
   {
     Geo           g;
@@ -94,6 +113,9 @@ namespace spirk
     double       *dst;
     const double *src, *x_old, *rhs, *dinv;
     double        cm[SPIRK_MAX_BLOCKS], cl[SPIRK_MAX_BLOCKS], f1[SPIRK_MAX_BLOCKS], f2[SPIRK_MAX_BLOCKS];
+    // A = sc (Mz My K'x + Mz K'y Mx + K'z My Mx) with K' = Kh + cm / (3 cl) Mh, sc = cl  (cl = 0: K' = Mh / 3, sc = cm):
+    // the mass term rides in the three stiffness terms, so no sweep scales its result
+    double        sc[SPIRK_MAX_BLOCKS], kp[SPIRK_MAX_BLOCKS][V3_NKP];
     int           ntx, nty;
     long long     W; // nb * columns * layers
     int           lock_nch, lock_len; // > 0: z-lockstep schedule (CTA = one column x one of lock_nch equal layer ranges)
@@ -158,9 +180,9 @@ namespace spirk
     double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K;
     uint64_t *BAR  = reinterpret_cast<uint64_t *>(SDI + K * K * K);
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
-    const double  Mv = c_fe[K].Mv, Kv = c_fe[K].Kv;
+    const double  Mv = c_fe[K].Mv;
 #define MC(i, j) Mh[v3_canon<K>(i, j)]
-#define KC(i, j) Kh[v3_canon<K>(i, j)]
+#define KC(i, j) kp[v3_cidx<K>(i, j)]
 
     const int       tid = threadIdx.x;
     const int       n1 = a.g.n1, nc = a.g.nc;
@@ -202,7 +224,9 @@ namespace spirk
         w += L1 - L0;
         const int       tx = col % a.ntx, ty = col / a.ntx;
         const int       gx0 = tx * OX, gy0 = ty * OY;
-        const double    cm = a.cm[b], cl = a.cl[b], f1 = a.f1[b], f2 = a.f2[b];
+        const double    cm = a.cm[b], cl = a.cl[b], f1 = a.f1[b], f2 = a.f2[b], sc = a.sc[b], sc_inv = 1.0 / sc;
+        const double   *kp = a.kp[b];
+        const double    Kv = kp[V3_NKP - 1];
         const long long boff = (long long)b * a.stride;
         const double   *src  = a.src + boff;
         const int       zf   = (L0 > 0) ? L0 - 1 : 0;      // first layer that is processed (recomputed if < L0)
@@ -217,12 +241,13 @@ namespace spirk
             for (int e = tid; e < K * K * K; e += NT)
               {
                 const int    cx = e % K, cy = (e / K) % K, cz = e / (K * K);
-                const double mx = cx ? Mh[cx * n + cx] : Mv, kx = cx ? Kh[cx * n + cx] : Kv;
-                const double my = cy ? Mh[cy * n + cy] : Mv, ky = cy ? Kh[cy * n + cy] : Kv;
-                const double mz = cz ? Mh[cz * n + cz] : Mv, kz = cz ? Kh[cz * n + cz] : Kv;
+                const double Kv0 = c_fe[K].Kv;
+                const double mx = cx ? Mh[cx * n + cx] : Mv, kx = cx ? Kh[cx * n + cx] : Kv0;
+                const double my = cy ? Mh[cy * n + cy] : Mv, ky = cy ? Kh[cy * n + cy] : Kv0;
+                const double mz = cz ? Mh[cz * n + cz] : Mv, kz = cz ? Kh[cz * n + cz] : Kv0;
                 const double d  = cm * mx * my * mz + cl * (kx * my * mz + mx * ky * mz + mx * my * kz);
                 const double di = (fabs(d) > 1.0e-10) ? 1.0 / d : 1.0;
-                SDS[e] = -f2 * di, SDI[e] = 1.0 / (f2 * di);
+                SDS[e] = -f2 * di * sc, SDI[e] = 1.0 / (f2 * di * sc);
               }
             b_tab = b;
           }
@@ -263,21 +288,7 @@ namespace spirk
                 }
             }
         };
-        // shared-memory offset of staged row r (0..LYS-1) / operand row ro (0..OY-1) of the plane of step s_:
-        // box of the row's parity, position inside the box, and the 8-byte parity of the row start (a box starts
-        // at the 16-byte aligned element at or below the first wanted one; gx0, K even, n1 odd)
         const int rb0_par = (int)(Rb0 & 1);
-        auto      urow    = [&](const int r, const int s_) {
-          const int par = (rb0_par + s_) & 1; // parity of the staged row 0 of this step (n1 is odd)
-          const int blk = (par + r) & 1;
-          // rows of parity `blk`: r = (par ^ blk), +2, ...: index (r - (par ^ blk)) / 2
-          return blk * UB + ((r - (par ^ blk)) >> 1) * BW + (a.sh_src ^ blk);
-        };
-        auto orow = [&](const int ro, const int s_, const int sh) {
-          const int par = (rb0_par + s_) & 1; // K is even: operand row 0 (= staged row K) has the same parity
-          const int blk = (par + ro) & 1;
-          return blk * OB + ((ro - (par ^ blk)) >> 1) * OW + (sh ^ blk);
-        };
 
         double acc[n][K]; // z-sums of the current layer: planes 0..K x the K owned nodes of this thread
 #pragma unroll
@@ -288,103 +299,122 @@ namespace spirk
 
         for (int s = 0; s < NBUF && s < nsteps; ++s)
           issue(s);
-        for (int s = 0; s < nsteps; ++s)
-          {
-            const unsigned slot = (it0 + s) % NBUF;
-            const int      P    = K * zf + s;
-            const bool     zpl  = (P <= 0) || (P >= n1 - 1);
-            const double  *ub   = RING + slot * SLOT;
-            double        *SA = AC + (NAC == 2 ? (s & 1) * (2 * LYS * PA) : 0), *SC = SA + LYS * PA;
-            while (!mbar_try_wait(bar_u32 + 8 * slot, ((it0 + s) / NBUF) & 1))
-              ;
-            if (NAC == 1)
-              __syncthreads(); // the a'/c tile of the previous plane is consumed
 
-            // -------------------------------------------------------------- x-phase
-            for (int q = tid; q < C::NXT; q += NT)
-              {
-                const int seg = q / LYS, row = q - seg * LYS;
-                const int gy  = gy0 - K + row;
-                double   *oa = SA + row * PA + K * seg, *oc = SC + row * PA + K * seg;
-                if (zpl || gy <= 0 || gy >= n1 - 1)
-                  {
+        // running state of the plane loop (kept incrementally: no div / mod per step)
+        unsigned slot = it0 % NBUF, phase = (it0 / NBUF) & 1; // ring slot of the plane and its mbarrier phase
+        int      par  = rb0_par;                             // parity of the staged row 0 of the plane (n1 is odd)
+        int      P    = K * zf;                              // node plane
+        int      sbuf = 0;                                   // a'/c tile buffer
+        int      s    = 0;
+
+        // one node plane; ZL = position of the plane in its cell layer (0 only for the first plane of a piece),
+        // Lc = the layer the plane belongs to as plane ZL (for ZL == K: the layer it completes)
+        auto step = [&](auto zl_c, const int Lc) {
+          constexpr int ZL  = decltype(zl_c)::value;
+          const bool    zpl = (P <= 0) || (P >= n1 - 1);
+          const double *ub  = RING + slot * SLOT;
+          double       *SA = AC + (NAC == 2 ? sbuf * (2 * LYS * PA) : 0), *SC = SA + LYS * PA;
+          // shared-memory offset of staged row r / operand row ro: box of the row's parity, position inside the box,
+          // and the 8-byte parity of the row start (a box starts at the 16-byte aligned element at or below the first
+          // wanted one; gx0, K even, n1 odd)
+          auto urow = [&](const int r) {
+            const int blk = (par + r) & 1;
+            return blk * UB + ((r - (par ^ blk)) >> 1) * BW + (a.sh_src ^ blk);
+          };
+          auto orow = [&](const int ro, const int sh) {
+            const int blk = (par + ro) & 1; // K is even: operand row 0 (= staged row K) has the parity of staged row 0
+            return blk * OB + ((ro - (par ^ blk)) >> 1) * OW + (sh ^ blk);
+          };
+          while (!mbar_try_wait(bar_u32 + 8 * slot, phase))
+            ;
+          if (NAC == 1)
+            __syncthreads(); // the a'/c tile of the previous plane is consumed
+
+          // -------------------------------------------------------------- x-phase: a = Mx u, c = K'x u
+          for (int q = tid; q < C::NXT; q += NT)
+            {
+              const int seg = q / LYS, row = q - seg * LYS;
+              const int gy  = gy0 - K + row;
+              double   *oa = SA + row * PA + K * seg, *oc = SC + row * PA + K * seg;
+              if (zpl || gy <= 0 || gy >= n1 - 1)
+                {
 #pragma unroll
-                    for (int i = 0; i < K; ++i)
-                      oa[i] = 0.0, oc[i] = 0.0;
-                  }
-                else
-                  {
-                    const double *ur = ub + urow(row, s) + K * seg;
-                    double        u[2 * K + 1];
+                  for (int i = 0; i < K; ++i)
+                    oa[i] = 0.0, oc[i] = 0.0;
+                }
+              else
+                {
+                  const double *ur = ub + urow(row) + K * seg;
+                  double        u[2 * K + 1];
 #pragma unroll
-                    for (int j = 0; j < 2 * K + 1; ++j)
-                      u[j] = ur[j];
-                    if (edge_x)
-                      {
-                        if (seg == 0 && tx == 0)
-                          { // x < 0 (outside) and x = 0 (Dirichlet)
-#pragma unroll
-                            for (int j = 0; j <= K; ++j)
-                              u[j] = 0.0;
-                          }
-                        if (seg == 1 && tx == 0)
-                          u[0] = 0.0; // x = 0 seen from the second cell
-                        if (seg == TX - 1 && tx == a.ntx - 1)
-                          u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
-                      }
-                    // vertex row: two partial sums each (short dependency chains)
-                    double am[K], ak[K];
+                  for (int j = 0; j < 2 * K + 1; ++j)
+                    u[j] = ur[j];
+                  if (edge_x)
                     {
-                      double m1 = MC(0, 1) * u[K + 1], k1 = KC(0, 1) * u[K + 1];
-                      am[0] = Mv * u[K], ak[0] = Kv * u[K];
+                      if (seg == 0 && tx == 0)
+                        { // x < 0 (outside) and x = 0 (Dirichlet)
 #pragma unroll
-                      for (int j = 0; j < K; ++j)
-                        am[0] = fma(MC(K, j), u[j], am[0]), ak[0] = fma(KC(K, j), u[j], ak[0]);
+                          for (int j = 0; j <= K; ++j)
+                            u[j] = 0.0;
+                        }
+                      if (seg == 1 && tx == 0)
+                        u[0] = 0.0; // x = 0 seen from the second cell
+                      if (seg == TX - 1 && tx == a.ntx - 1)
+                        u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
+                    }
+                  // vertex row: two partial sums each (short dependency chains)
+                  double am[K], ak[K];
+                  {
+                    double m1 = MC(0, 1) * u[K + 1], k1 = KC(0, 1) * u[K + 1];
+                    am[0] = Mv * u[K], ak[0] = Kv * u[K];
 #pragma unroll
-                      for (int j = 2; j <= K; ++j)
-                        m1 = fma(MC(0, j), u[K + j], m1), k1 = fma(KC(0, j), u[K + j], k1);
-                      am[0] += m1, ak[0] += k1;
+                    for (int j = 0; j < K; ++j)
+                      am[0] = fma(MC(K, j), u[j], am[0]), ak[0] = fma(KC(K, j), u[j], ak[0]);
+#pragma unroll
+                    for (int j = 2; j <= K; ++j)
+                      m1 = fma(MC(0, j), u[K + j], m1), k1 = fma(KC(0, j), u[K + j], k1);
+                    am[0] += m1, ak[0] += k1;
+                  }
+#pragma unroll
+                  for (int i = 1; i < K; ++i)
+                    {
+                      am[i] = MC(i, 0) * u[K], ak[i] = KC(i, 0) * u[K];
+#pragma unroll
+                      for (int j = 1; j <= K; ++j)
+                        am[i] = fma(MC(i, j), u[K + j], am[i]), ak[i] = fma(KC(i, j), u[K + j], ak[i]);
                     }
 #pragma unroll
-                    for (int i = 1; i < K; ++i)
-                      {
-                        am[i] = MC(i, 0) * u[K], ak[i] = KC(i, 0) * u[K];
-#pragma unroll
-                        for (int j = 1; j <= K; ++j)
-                          am[i] = fma(MC(i, j), u[K + j], am[i]), ak[i] = fma(KC(i, j), u[K + j], ak[i]);
-                      }
-#pragma unroll
-                    for (int i = 0; i < K; ++i)
-                      oa[i] = cl * am[i], oc[i] = fma(cm, am[i], cl * ak[i]);
-                  }
-              }
-            __syncthreads();
-            // the slot of the previous plane is free now (its operands were read in the previous y+z phase)
-            if (s >= 1 && s - 1 + NBUF < nsteps)
-              issue(s - 1 + NBUF);
+                  for (int i = 0; i < K; ++i)
+                    oa[i] = am[i], oc[i] = ak[i];
+                }
+            }
+          __syncthreads();
+          // the slot of the previous plane is free now (its operands were read in the previous y+z phase)
+          if (s >= 1 && s - 1 + NBUF < nsteps)
+            issue(s - 1 + NBUF);
 
-            if (is_yz)
-              {
-              // -------------------------------------------------------------- y-sweep
+          if (is_yz)
+            {
+              // -------------------------------------------------------------- y-sweep: p = My a, w = My c + K'y a
               double p[K], wv[K];
               {
                 const double *ar = SA + (K * ys) * PA + xl, *cr = SC + (K * ys) * PA + xl;
                 double        av[2 * K + 1], cv[2 * K + 1];
-  #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 2 * K + 1; ++j)
                   av[j] = ar[j * PA], cv[j] = cr[j * PA];
-                // vertex row: four partial sums for w, two for p'; interior rows: M c and K a' separately
+                // vertex row: four partial sums for w, two for p; interior rows: M c and K' a separately
                 {
                   double p1 = MC(0, 1) * av[K + 1], wm1 = MC(0, 1) * cv[K + 1], wk0 = Kv * av[K], wk1 = KC(0, 1) * av[K + 1];
                   p[0] = Mv * av[K], wv[0] = Mv * cv[K];
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < K; ++j)
                     {
                       p[0]  = fma(MC(K, j), av[j], p[0]);
                       wv[0] = fma(MC(K, j), cv[j], wv[0]);
                       wk0   = fma(KC(K, j), av[j], wk0);
                     }
-  #pragma unroll
+#pragma unroll
                   for (int j = 2; j <= K; ++j)
                     {
                       p1  = fma(MC(0, j), av[K + j], p1);
@@ -393,12 +423,12 @@ namespace spirk
                     }
                   p[0] += p1, wv[0] = (wv[0] + wm1) + (wk0 + wk1);
                 }
-  #pragma unroll
+#pragma unroll
                 for (int i = 1; i < K; ++i)
                   {
                     double wk = KC(i, 0) * av[K];
                     p[i] = MC(i, 0) * av[K], wv[i] = MC(i, 0) * cv[K];
-  #pragma unroll
+#pragma unroll
                     for (int j = 1; j <= K; ++j)
                       {
                         p[i]  = fma(MC(i, j), av[K + j], p[i]);
@@ -409,61 +439,54 @@ namespace spirk
                   }
               }
               // -------------------------------------------------------------- linear part of the epilogue of this plane
-              // g = rhs (residual) | rhs + ((1 + f1) x - f1 x_old) / (f2 dinv) (Chebyshev); the z-sums run on A x - g
-              const int  zl    = (s == 0) ? 0 : ((s - 1) % K) + 1;
-              const bool owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+              // the z-sums run on (A x) / sc - g with  g = rhs / sc (residual) | (rhs + ((1 + f1) x - f1 x_old) / (f2 dinv)) / sc
+              // (Chebyshev); sc = the scalar factored out of the operator (see v3_apply)
+              const bool owned = (NOPS > 0) && (ZL > 0) && !zpl && (P >= K * L0) && (P < K * L1);
               double     g[K];
-  #pragma unroll
+#pragma unroll
               for (int i = 0; i < K; ++i)
                 g[i] = 0.0;
               if (NOPS > 0 && owned)
                 {
                   if (MODE == V2_RESIDUAL)
                     {
-  #pragma unroll
+#pragma unroll
                       for (int i = 0; i < K; ++i)
-                        g[i] = ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl];
+                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i, a.sh_o0) + xl];
                     }
                   else
                     {
-                      const double *sdi = SDI + ((P % K) * K) * K + (xl % K);
-  #pragma unroll
+                      const double *sdi = SDI + ((ZL % K) * K) * K + (xl % K);
+#pragma unroll
                       for (int i = 0; i < K; ++i)
                         {
-                          const double x  = ub[urow(K + K * ys + i, s) + K + xl];
-                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, s, a.sh_o0) + xl] : 0.0;
-                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, s, a.sh_o1) + xl];
-                          g[i]             = fma(fma(f1, x - xo, x), sdi[i * K], rh);
+                          const double x  = ub[urow(K + K * ys + i) + K + xl];
+                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, a.sh_o0) + xl] : 0.0;
+                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, a.sh_o1) + xl];
+                          g[i]            = fma(fma(f1, x - xo, x), sdi[i * K], sc_inv * rh);
                         }
                     }
                 }
-              // -------------------------------------------------------------- z-accumulation
-              if (zl < K)
+              // -------------------------------------------------------------- z-accumulation: out = Mz w + K'z p
+              if constexpr (ZL < K)
                 {
-                  // columns 0..K-1 of the cell matrices (uniform switch keeps the entries in few registers)
-  #pragma unroll
-                  for (int zz = 0; zz < K; ++zz)
-                    if (zl == zz)
-                      {
-  #pragma unroll
-                        for (int z = 0; z < n; ++z)
-  #pragma unroll
-                          for (int i = 0; i < K; ++i)
-                            acc[z][i] = fma(MC(z, zz), wv[i], fma(KC(z, zz), p[i], acc[z][i]));
-                        if (NOPS > 0 && zz > 0)
-                          {
-  #pragma unroll
-                            for (int i = 0; i < K; ++i)
-                              acc[zz][i] -= g[i];
-                          }
-                      }
+#pragma unroll
+                  for (int z = 0; z < n; ++z)
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
+                  if (NOPS > 0 && ZL > 0)
+                    {
+#pragma unroll
+                      for (int i = 0; i < K; ++i)
+                        acc[ZL][i] -= g[i];
+                    }
                 }
               else
                 {
-                  const int Lc = zf + (s - 1) / K; // the layer that this (top) plane completes
-  #pragma unroll
+#pragma unroll
                   for (int z = 0; z < n; ++z)
-  #pragma unroll
+#pragma unroll
                     for (int i = 0; i < K; ++i)
                       acc[z][i] = fma(MC(z, K), wv[i], fma(KC(z, K), p[i], acc[z][i]));
                   if (Lc >= L0)
@@ -474,9 +497,9 @@ namespace spirk
                       if (MODE == V2_CHEB)
                         {
                           // explicit inverse diagonal: operands straight from global memory
-  #pragma unroll
+#pragma unroll
                           for (int z = 0; z < K; ++z)
-  #pragma unroll
+#pragma unroll
                             for (int i = 0; i < K; ++i)
                               {
                                 const long long j = j0 + z * plane + i * n1;
@@ -485,7 +508,7 @@ namespace spirk
                                 else
                                   {
                                     const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
-                                    a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - acc[z][i], fma(f1, x - xo, x));
+                                    a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - sc * acc[z][i], fma(f1, x - xo, x));
                                   }
                               }
                         }
@@ -493,58 +516,75 @@ namespace spirk
                         {
                           double       *dp  = a.dst + j0;
                           const double *sds = SDS + (xl % K);
+                          const double  sca = (MODE == V2_APPLY) ? sc : -sc;
                           if (!anyb)
                             {
-  #pragma unroll
+#pragma unroll
                               for (int z = 0; z < K; ++z)
-  #pragma unroll
+#pragma unroll
                                 for (int i = 0; i < K; ++i)
-                                  dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
-                                                           : (MODE == V2_RESIDUAL) ? -acc[z][i]
-                                                                                   : sds[(z * K + i) * K] * acc[z][i];
+                                  dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN) ? sds[(z * K + i) * K] : sca) * acc[z][i];
                             }
                           else
                             {
-  #pragma unroll
+#pragma unroll
                               for (int z = 0; z < K; ++z)
-  #pragma unroll
+#pragma unroll
                                 for (int i = 0; i < K; ++i)
                                   {
                                     if ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0))
                                       v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1);
                                     else
-                                      dp[z * plane + i * n1] = (MODE == V2_APPLY)      ? acc[z][i]
-                                                               : (MODE == V2_RESIDUAL) ? -acc[z][i]
-                                                                                       : sds[(z * K + i) * K] * acc[z][i];
+                                      dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN) ? sds[(z * K + i) * K] : sca) * acc[z][i];
                                   }
                             }
                         }
                     }
                   // the top plane becomes the bottom plane of the next layer
-  #pragma unroll
+#pragma unroll
                   for (int i = 0; i < K; ++i)
                     {
                       acc[0][i] = fma(MC(0, 0), wv[i], fma(KC(0, 0), p[i], acc[K][i])) - g[i];
-  #pragma unroll
+#pragma unroll
                       for (int z = 1; z < n; ++z)
                         acc[z][i] = fma(MC(z, 0), wv[i], KC(z, 0) * p[i]);
                     }
                 }
-                        }
-            if (!is_yz && s > 0 && (s - 1) % K == K - 1 && zf + (s - 1) / K >= L0)
-              {
-                // helpers: Dirichlet faces x = n1-1 and y = n1-1 of the K planes of the completed layer (owned by no tile)
-                const int Lc = zf + (s - 1) / K, ht = tid - NY;
-                if (tx == a.ntx - 1)
-                  {
-                    const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
-                    for (int e = ht; e < K * oye; e += NH)
-                      v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye));
-                  }
-                if (ty == a.nty - 1)
-                  for (int e = ht; e < K * OX; e += NH)
-                    v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
-              }
+            }
+          else if (ZL == K && Lc >= L0)
+            {
+              // helpers: Dirichlet faces x = n1-1 and y = n1-1 of the K planes of the completed layer (owned by no tile)
+              const int ht = tid - NY;
+              if (tx == a.ntx - 1)
+                {
+                  const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
+                  for (int e = ht; e < K * oye; e += NH)
+                    v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye));
+                }
+              if (ty == a.nty - 1)
+                for (int e = ht; e < K * OX; e += NH)
+                  v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
+            }
+          // advance the running state
+          ++s, ++P, par ^= 1, sbuf ^= 1;
+          if (++slot == NBUF)
+            slot = 0, phase ^= 1;
+        };
+
+        step(std::integral_constant<int, 0>{}, zf);
+        for (int Lc = zf; Lc < L1; ++Lc)
+          {
+            step(std::integral_constant<int, 1>{}, Lc);
+            if constexpr (K >= 2)
+              step(std::integral_constant<int, (K >= 2 ? 2 : 1)>{}, Lc);
+            if constexpr (K >= 3)
+              step(std::integral_constant<int, (K >= 3 ? 3 : 1)>{}, Lc);
+            if constexpr (K >= 4)
+              step(std::integral_constant<int, (K >= 4 ? 4 : 1)>{}, Lc);
+            if constexpr (K >= 5)
+              step(std::integral_constant<int, (K >= 5 ? 5 : 1)>{}, Lc);
+            if constexpr (K >= 6)
+              step(std::integral_constant<int, (K >= 6 ? 6 : 1)>{}, Lc);
           }
         it0 += nsteps;
         // top plane of the domain (Dirichlet)
@@ -681,12 +721,24 @@ namespace spirk
     a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1;
     a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = dinv;
     const double hd = g.h * g.h * g.h, hl = g.h;
+    constexpr int K = 4, n = K + 1;
+    double        Ms[n * n], Ks[n * n];
+    fe_host_sym(K, Ms, Ks);
     for (int b = 0; b < op->nb; ++b)
       {
         a.cm[b] = op->mass[b] * hd, a.cl[b] = op->laplace[b] * hl;
         a.f1[b] = f1 ? f1[b] : 0.0, a.f2[b] = f2 ? f2[b] : 0.0;
         if (mode >= V2_CHEB && dinv == nullptr && a.f2[b] == 0.0)
           return SPIRK_ERR_UNSUPPORTED; // the folded Chebyshev epilogue divides by f2
+        if (a.cm[b] == 0.0 && a.cl[b] == 0.0)
+          return SPIRK_ERR_UNSUPPORTED; // the zero operator has no scalar to factor out
+        const bool   lap   = (a.cl[b] != 0.0);
+        const double gamma = lap ? a.cm[b] / (3.0 * a.cl[b]) : 0.0;
+        a.sc[b]            = lap ? a.cl[b] : a.cm[b];
+        for (int i = 0; i < n; ++i)
+          for (int j = 0; j < n; ++j)
+            a.kp[b][v3_cidx<K>(i, j)] = lap ? Ks[i * n + j] + gamma * Ms[i * n + j] : Ms[i * n + j] / 3.0;
+        a.kp[b][V3_NKP - 1] = a.kp[b][v3_cidx<K>(K, K)] + a.kp[b][v3_cidx<K>(0, 0)];
       }
     return v3_launch<4, 8, 8>(ctx, a, mode);
   }

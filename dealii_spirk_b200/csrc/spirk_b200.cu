@@ -66,6 +66,19 @@ namespace spirk
     return SPIRK_OK;
   }
 
+  void fe_host_sym(int k, double *Mh, double *Kh)
+  {
+    init_fe_host();
+    const Fe1D &f = g_fe[k];
+    const int   n = f.n;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j)
+        {
+          Mh[i * n + j] = 0.5 * (f.Mh[i * n + j] + f.Mh[(k - i) * n + (k - j)]);
+          Kh[i * n + j] = 0.5 * (f.Kh[i * n + j] + f.Kh[(k - i) * n + (k - j)]);
+        }
+  }
+
   int ensure_scratch(spirk_ctx *ctx, size_t n)
   {
     if (ctx->scratch_cap < n)
