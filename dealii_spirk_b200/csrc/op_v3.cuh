@@ -60,15 +60,33 @@ namespace spirk
     static constexpr int OB   = OW * (OY / 2);
     static constexpr int PA   = OX | 1;         // odd pitch: lanes along y hit distinct banks
     static constexpr int NOPS = v3_nops(MODE);  // operand planes that travel with the staged plane
+#ifdef SPIRK_V3_EXPERIMENT_MINB
+    static constexpr int NBUF = 3;
+#else
     static constexpr int NBUF = (NOPS == 0) ? 4 : 3; // ring depth (three / two planes in flight; 2 CTAs per SM must fit)
+#endif
+#ifdef SPIRK_V3_EXPERIMENT_MINB
+    static constexpr int NAC = 1;
+#else
     static constexpr int NAC  = (NOPS == 2) ? 1 : 2; // a'/c tile double-buffered where shared memory allows
+#endif
+    // software pipeline: the x-phase of plane s + 1 runs in the same barrier interval as the y+z phase of plane s
+    // (one __syncthreads per plane, two independent tasks per thread); needs the double-buffered tile
+#ifndef SPIRK_V3_PIPE
+#define SPIRK_V3_PIPE 0
+#endif
+    static constexpr bool PIPE = (NAC == 2) && (SPIRK_V3_PIPE != 0);
     static constexpr int SLOT = 2 * UB + NOPS * 2 * OB;
     static constexpr int NY   = OX * TY;  // y+z tasks (one thread each)
     static constexpr int NXT  = LYS * TX; // x-phase tasks
     static constexpr int NT   = ((NXT > NY ? NXT : NY) + 31) / 32 * 32; // one x task per thread; the threads beyond NY are helpers:
                                                                          // TMA issue, Dirichlet faces
     static constexpr int NH   = NT - NY;
+#ifdef SPIRK_V3_EXPERIMENT_MINB
+    static constexpr int MINB = SPIRK_V3_EXPERIMENT_MINB;
+#else
     static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 4 : 8);
+#endif
     static constexpr unsigned BYTES_U = 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
     static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
     static_assert(NY % 32 == 0 && NT <= 1024 && NH >= 32, "tile shape");
@@ -309,34 +327,31 @@ namespace spirk
 
         // one node plane; ZL = position of the plane in its cell layer (0 only for the first plane of a piece),
         // Lc = the layer the plane belongs to as plane ZL (for ZL == K: the layer it completes)
-        auto step = [&](auto zl_c, const int Lc) {
-          constexpr int ZL  = decltype(zl_c)::value;
-          const bool    zpl = (P <= 0) || (P >= n1 - 1);
-          const double *ub  = RING + slot * SLOT;
-          double       *SA = AC + (NAC == 2 ? sbuf * (2 * LYS * PA) : 0), *SC = SA + LYS * PA;
-          // shared-memory offset of staged row r / operand row ro: box of the row's parity, position inside the box,
-          // and the 8-byte parity of the row start (a box starts at the 16-byte aligned element at or below the first
-          // wanted one; gx0, K even, n1 odd)
-          auto urow = [&](const int r) {
-            const int blk = (par + r) & 1;
-            return blk * UB + ((r - (par ^ blk)) >> 1) * BW + (a.sh_src ^ blk);
-          };
-          auto orow = [&](const int ro, const int sh) {
-            const int blk = (par + ro) & 1; // K is even: operand row 0 (= staged row K) has the parity of staged row 0
-            return blk * OB + ((ro - (par ^ blk)) >> 1) * OW + (sh ^ blk);
-          };
-          while (!mbar_try_wait(bar_u32 + 8 * slot, phase))
+        // shared-memory offset of staged row r / operand row ro of a plane whose staged row 0 has parity par_: box of the
+        // row's parity, position inside the box, and the 8-byte parity of the row start (a box starts at the 16-byte
+        // aligned element at or below the first wanted one; gx0, K even, n1 odd)
+        auto urow = [&](const int r, const int par_) {
+          const int blk = (par_ + r) & 1;
+          return blk * UB + ((r - (par_ ^ blk)) >> 1) * BW + (a.sh_src ^ blk);
+        };
+        auto orow = [&](const int ro, const int par_, const int sh) {
+          const int blk = (par_ + ro) & 1; // K is even: operand row 0 (= staged row K) has the parity of staged row 0
+          return blk * OB + ((ro - (par_ ^ blk)) >> 1) * OW + (sh ^ blk);
+        };
+        // x-phase of the plane xP staged in ring slot xslot: a = Mx u, c = K'x u into the tile buffer xbuf
+        auto xphase = [&](const unsigned xslot, const unsigned xphase_bit, const int xpar, const int xP, const int xbuf) {
+          const bool    xzpl = (xP <= 0) || (xP >= n1 - 1);
+          const double *xub  = RING + xslot * SLOT;
+          double       *XA = AC + (NAC == 2 ? xbuf * (2 * LYS * PA) : 0), *XC = XA + LYS * PA;
+          while (!mbar_try_wait(bar_u32 + 8 * xslot, xphase_bit))
             ;
-          if (NAC == 1)
-            __syncthreads(); // the a'/c tile of the previous plane is consumed
-
           // -------------------------------------------------------------- x-phase: a = Mx u, c = K'x u
           for (int q = tid; q < C::NXT; q += NT)
             {
               const int seg = q / LYS, row = q - seg * LYS;
               const int gy  = gy0 - K + row;
-              double   *oa = SA + row * PA + K * seg, *oc = SC + row * PA + K * seg;
-              if (zpl || gy <= 0 || gy >= n1 - 1)
+              double   *oa = XA + row * PA + K * seg, *oc = XC + row * PA + K * seg;
+              if (xzpl || gy <= 0 || gy >= n1 - 1)
                 {
 #pragma unroll
                   for (int i = 0; i < K; ++i)
@@ -344,7 +359,7 @@ namespace spirk
                 }
               else
                 {
-                  const double *ur = ub + urow(row) + K * seg;
+                  const double *ur = xub + urow(row, xpar) + K * seg;
                   double        u[2 * K + 1];
 #pragma unroll
                   for (int j = 0; j < 2 * K + 1; ++j)
@@ -388,10 +403,34 @@ namespace spirk
                     oa[i] = am[i], oc[i] = ak[i];
                 }
             }
-          __syncthreads();
-          // the slot of the previous plane is free now (its operands were read in the previous y+z phase)
-          if (s >= 1 && s - 1 + NBUF < nsteps)
-            issue(s - 1 + NBUF);
+        };
+
+        // one node plane; ZL = position of the plane in its cell layer (0 only for the first plane of a piece),
+        // Lc = the layer the plane belongs to as plane ZL (for ZL == K: the layer it completes)
+        auto step = [&](auto zl_c, const int Lc) {
+          constexpr int ZL  = decltype(zl_c)::value;
+          const bool    zpl = (P <= 0) || (P >= n1 - 1);
+          const double *ub  = RING + slot * SLOT;
+          const double *SA = AC + (NAC == 2 ? sbuf * (2 * LYS * PA) : 0), *SC = SA + LYS * PA;
+          if (C::PIPE)
+            {
+              // the tile of this plane was filled in the previous interval; fill the other buffer with the next plane
+              if (s + 1 < nsteps)
+                {
+                  const unsigned nslot = (slot + 1 == NBUF) ? 0 : slot + 1;
+                  xphase(nslot, (nslot == 0) ? phase ^ 1 : phase, par ^ 1, P + 1, sbuf ^ 1);
+                }
+            }
+          else
+            {
+              if (NAC == 1)
+                __syncthreads(); // the a'/c tile of the previous plane is consumed
+              xphase(slot, phase, par, P, sbuf);
+              __syncthreads();
+              // the slot of the previous plane is free now (its operands were read in the previous y+z phase)
+              if (s >= 1 && s - 1 + NBUF < nsteps)
+                issue(s - 1 + NBUF);
+            }
 
           if (is_yz)
             {
@@ -452,7 +491,7 @@ namespace spirk
                     {
 #pragma unroll
                       for (int i = 0; i < K; ++i)
-                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i, a.sh_o0) + xl];
+                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i, par, a.sh_o0) + xl];
                     }
                   else
                     {
@@ -460,9 +499,9 @@ namespace spirk
 #pragma unroll
                       for (int i = 0; i < K; ++i)
                         {
-                          const double x  = ub[urow(K + K * ys + i) + K + xl];
-                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, a.sh_o0) + xl] : 0.0;
-                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, a.sh_o1) + xl];
+                          const double x  = ub[urow(K + K * ys + i, par) + K + xl];
+                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, par, a.sh_o0) + xl] : 0.0;
+                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, par, a.sh_o1) + xl];
                           g[i]            = fma(fma(f1, x - xo, x), sdi[i * K], sc_inv * rh);
                         }
                     }
@@ -565,12 +604,23 @@ namespace spirk
                 for (int e = ht; e < K * OX; e += NH)
                   v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
             }
+          if (C::PIPE)
+            {
+              __syncthreads(); // the next tile is complete; this plane's ring slot and tile buffer are free
+              if (s + NBUF < nsteps)
+                issue(s + NBUF);
+            }
           // advance the running state
           ++s, ++P, par ^= 1, sbuf ^= 1;
           if (++slot == NBUF)
             slot = 0, phase ^= 1;
         };
 
+        if (C::PIPE)
+          {
+            xphase(slot, phase, par, P, sbuf);
+            __syncthreads();
+          }
         step(std::integral_constant<int, 0>{}, zf);
         for (int Lc = zf; Lc < L1; ++Lc)
           {
