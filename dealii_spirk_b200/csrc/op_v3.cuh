@@ -85,7 +85,7 @@ namespace spirk
 #ifdef SPIRK_V3_EXPERIMENT_MINB
     static constexpr int MINB = SPIRK_V3_EXPERIMENT_MINB;
 #else
-    static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 4 : 8);
+    static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 3 : 6);
 #endif
     static constexpr unsigned BYTES_U = 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
     static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
@@ -681,6 +681,22 @@ namespace spirk
   inline int v3_make_map(CUtensorMap *map, int *shift, const double *ptr, const long long n_elems, const int n1, const int box_w,
                          const int box_h)
   {
+    // the solver applies the operator to the same few vectors over and over: keep the encoded maps
+    struct Entry
+    {
+      const double *ptr;
+      long long     n_elems;
+      int           n1, box_w, box_h, shift;
+      CUtensorMap   map;
+    };
+    static thread_local std::vector<Entry> cache;
+    static thread_local size_t             next = 0;
+    for (const Entry &e : cache)
+      if (e.ptr == ptr && e.n_elems == n_elems && e.n1 == n1 && e.box_w == box_w && e.box_h == box_h)
+        {
+          *map = e.map, *shift = e.shift;
+          return SPIRK_OK;
+        }
     PFN_tmap_encode_tiled enc = v3_encode_fn();
     if (!enc)
       return set_error(SPIRK_ERR_DEVICE, "cuTensorMapEncodeTiled is not available");
@@ -690,10 +706,17 @@ namespace spirk
     const cuuint64_t dims[2]    = {(cuuint64_t)2 * n1, (cuuint64_t)((n_elems + *shift) / (2LL * n1))};
     const cuuint64_t strides[1] = {(cuuint64_t)2 * n1 * sizeof(double)};
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
-    const CUresult   r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    alignas(64) CUtensorMap tm;
+    const CUresult   r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)v3_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
       return set_error(SPIRK_ERR_DEVICE, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    *map = tm;
+    Entry e{ptr, n_elems, n1, box_w, box_h, *shift, tm};
+    if (cache.size() < 64)
+      cache.push_back(e);
+    else
+      cache[next++ % 64] = e;
     return SPIRK_OK;
   }
 
@@ -763,7 +786,7 @@ namespace spirk
                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
                       const double *f2)
   {
-    if (g.dim != 3 || g.k != 4 || op->kind != SPIRK_OP_REAL || g.nc % 8 != 0 || g.nc < 8)
+    if (g.dim != 3 || g.k != 4 || op->kind != SPIRK_OP_REAL || g.nc % 4 != 0 || g.nc < 8)
       return SPIRK_ERR_UNSUPPORTED;
     if (op->nb > 1 && stride % g.n1 != 0)
       return SPIRK_ERR_UNSUPPORTED; // the blocks must continue the row sequence of block 0 (one tensor map)
@@ -790,6 +813,16 @@ namespace spirk
             a.kp[b][v3_cidx<K>(i, j)] = lap ? Ks[i * n + j] + gamma * Ms[i * n + j] : Ms[i * n + j] / 3.0;
         a.kp[b][V3_NKP - 1] = a.kp[b][v3_cidx<K>(K, K)] + a.kp[b][v3_cidx<K>(0, 0)];
       }
+    // 8 x 8-cell tiles (37/32 halo) on large levels; 4 x 4-cell tiles (21/16 halo, 4 x the columns) keep all SMs busy on
+    // the coarser multigrid levels
+    static int small_below = -1;
+    if (small_below < 0)
+      {
+        const char *e = getenv("SPIRK_V3_SMALL_BELOW"); // tuning knob: levels with fewer cells per direction use 4 x 4 tiles
+        small_below   = e ? atoi(e) : 64;
+      }
+    if (g.nc % 8 != 0 || g.nc < small_below)
+      return v3_launch<4, 4, 4>(ctx, a, mode);
     return v3_launch<4, 8, 8>(ctx, a, mode);
   }
 } // namespace spirk
