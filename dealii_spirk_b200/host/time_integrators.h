@@ -13,6 +13,7 @@
 // the same classes cover 1 GPU (all stages batched on one device) up to one stage per GPU.
 #pragma once
 #include <chrono>
+#include <cstdlib>
 #include <functional>
 #include <iostream>
 #include <tuple>
@@ -368,10 +369,51 @@ namespace spirk_host
             mix_rows(dst, src, Tm, 0, n_stages, add, cutoff);
             return;
           }
+        if (peer_exchange(src))
+          {
+            // fused all-gather + mixing: every rank publishes its stage blocks in a peer-mapped exchange buffer and
+            // ONE kernel contracts over all stages reading the remote blocks over NVLink (the reference's MPI-3
+            // shared-memory variant, main.cc:1506-1533); no gathered copy is written
+            const long long n = src.block_size();
+            SPIRK_CHECK(spirk_vec_copy(src.ctx(), spirk_comm_xbuf_local(xbuf), src.data(), n * m_local));
+            std::vector<double> rows((size_t)m_local * Tm.n());
+            for (unsigned int i = 0; i < m_local; ++i)
+              for (unsigned int j = 0; j < Tm.n(); ++j)
+                rows[(size_t)i * Tm.n() + j] = Tm(s0 + i, j);
+            SPIRK_CHECK(spirk_mix_peer(src.ctx(), row.comm, xbuf, (int)m_local, (int)m_local, dst.data(), dst.block_size(), n,
+                                       rows.data(), add ? 1 : 0, cutoff));
+            return;
+          }
         gathered.reinit(src.device(), src.block_size(), n_stages, true);
         row.all_gather(gathered, src);
         mix_rows(dst, gathered, Tm, s0, m_local, add, cutoff);
       }
+
+      // peer-mapped exchange buffer of the stage group (created on first use; SPIRK_PEER_MIX=0 keeps NCCL all-gather)
+      bool peer_exchange(const Vector &src) const
+      {
+        if (xbuf_state == 0)
+          {
+            const char *e = std::getenv("SPIRK_PEER_MIX");
+            xbuf_state    = 2;
+            if (!(e && std::atoi(e) == 0))
+              {
+                const int st = spirk_comm_xbuf_create(src.ctx(), row.comm, src.block_size() * m_local, &xbuf);
+                // all ranks must agree (a rank without peer access falls back together with the others)
+                const double ok = row.sum(src.device(), st == SPIRK_OK ? 0.0 : 1.0);
+                if (ok == 0.0)
+                  xbuf_state = 1;
+                else if (st == SPIRK_OK)
+                  {
+                    spirk_comm_xbuf_destroy(src.ctx(), xbuf);
+                    xbuf = nullptr;
+                  }
+              }
+          }
+        return xbuf_state == 1;
+      }
+      mutable spirk_xbuf *xbuf       = nullptr;
+      mutable int         xbuf_state = 0; // 0: not tried, 1: peer exchange, 2: NCCL all-gather
 
       struct SystemMatrix
       {
