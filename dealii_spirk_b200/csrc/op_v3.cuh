@@ -49,7 +49,7 @@ namespace spirk
 {
   __host__ __device__ constexpr int v3_nops(const int mode) { return mode == V2_RESIDUAL ? 1 : (mode == V2_CHEB_OWN ? 2 : 0); }
 
-  template <int K, int TX, int TY, int MODE>
+  template <int K, int TX, int TY, int MODE, int NPT = K>
   struct CfgV3
   {
     static constexpr int n = K + 1, OX = K * TX, OY = K * TY, LXS = OX + K + 1, LYS = OY + K + 1;
@@ -77,7 +77,8 @@ namespace spirk
 #endif
     static constexpr bool PIPE = (NAC == 2) && (SPIRK_V3_PIPE != 0);
     static constexpr int SLOT = 2 * UB + NOPS * 2 * OB;
-    static constexpr int NY   = OX * TY;  // y+z tasks (one thread each)
+    static constexpr int NHALF = K / NPT;          // a cell segment in y is shared by NHALF threads of NPT nodes each
+    static constexpr int NY   = OX * TY * NHALF; // y+z tasks (one thread each)
     static constexpr int NXT  = LYS * TX; // x-phase tasks
     static constexpr int NT   = ((NXT > NY ? NXT : NY) + 31) / 32 * 32; // one x task per thread; the threads beyond NY are helpers:
                                                                          // TMA issue, Dirichlet faces
@@ -89,7 +90,8 @@ namespace spirk
 #endif
     static constexpr unsigned BYTES_U = 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
     static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
-    static_assert(NY % 32 == 0 && NT <= 1024 && NH >= 32, "tile shape");
+    static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0, "tile shape");
+    static constexpr int ISSUER = (NH > 0) ? NY : 0; // the thread that issues the TMA copies
     static_assert(UB % 16 == 0 && OB % 16 == 0 && OY % 2 == 0 && BW <= 256 && BH <= 256, "128-byte aligned TMA boxes");
   };
 
@@ -187,10 +189,10 @@ namespace spirk
       }
   }
 
-  template <int K, int TX, int TY, int MODE>
-  __global__ void __launch_bounds__(CfgV3<K, TX, TY, MODE>::NT, CfgV3<K, TX, TY, MODE>::MINB) k_v3(const __grid_constant__ V3Args a)
+  template <int K, int TX, int TY, int MODE, int NPT>
+  __global__ void __launch_bounds__(CfgV3<K, TX, TY, MODE, NPT>::NT, CfgV3<K, TX, TY, MODE, NPT>::MINB) k_v3(const __grid_constant__ V3Args a)
   {
-    using C = CfgV3<K, TX, TY, MODE>;
+    using C = CfgV3<K, TX, TY, MODE, NPT>;
     constexpr int n = C::n, OX = C::OX, OY = C::OY, LYS = C::LYS, BW = C::BW, UB = C::UB, OW = C::OW, OB = C::OB, PA = C::PA, NT = C::NT;
     constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT, NY = C::NY, NH = C::NH;
     extern __shared__ __align__(16) double sm3_raw[];
@@ -207,7 +209,8 @@ namespace spirk
     const long long plane = (long long)n1 * n1;
     const int       ncols = a.ntx * a.nty;
     const bool      is_yz = tid < NY;                    // the other threads only take an x task, the TMA issue and the faces
-    const int       xl = tid % OX, ys = (tid / OX) % TY; // y+z task: owned x, cell segment in y
+    const int       xl = tid % OX, ys = (tid / OX) % TY; // y+z task: owned x, cell segment in y,
+    const int       half = (tid / OX) / TY, i0 = half * NPT; // ... and which NPT of its K nodes (warp-uniform)
 
     if (tid == 0)
       {
@@ -277,7 +280,7 @@ namespace spirk
         const long long Rb0 = (long long)b * a.rows_per_block + (long long)n1 * (K * zf) + (gy0 - K); // staged row 0 of step 0
         const bool      has_o0 = (MODE == V2_RESIDUAL) || (MODE == V2_CHEB_OWN && has_xo);
         auto            issue  = [&](const int sidx) {
-          if (tid == NY)
+          if (tid == C::ISSUER)
             {
               const int       P     = K * zf + sidx;
               const unsigned  slot  = (it0 + sidx) % NBUF;
@@ -308,11 +311,11 @@ namespace spirk
         };
         const int rb0_par = (int)(Rb0 & 1);
 
-        double acc[n][K]; // z-sums of the current layer: planes 0..K x the K owned nodes of this thread
+        double acc[n][NPT]; // z-sums of the current layer: planes 0..K x the NPT owned nodes of this thread
 #pragma unroll
         for (int z = 0; z < n; ++z)
 #pragma unroll
-          for (int i = 0; i < K; ++i)
+          for (int i = 0; i < NPT; ++i)
             acc[z][i] = 0.0;
 
         for (int s = 0; s < NBUF && s < nsteps; ++s)
@@ -435,73 +438,107 @@ namespace spirk
           if (is_yz)
             {
               // -------------------------------------------------------------- y-sweep: p = My a, w = My c + K'y a
-              double p[K], wv[K];
+              double p[NPT], wv[NPT];
               {
                 const double *ar = SA + (K * ys) * PA + xl, *cr = SC + (K * ys) * PA + xl;
-                double        av[2 * K + 1], cv[2 * K + 1];
 #pragma unroll
-                for (int j = 0; j < 2 * K + 1; ++j)
-                  av[j] = ar[j * PA], cv[j] = cr[j * PA];
-                // vertex row: four partial sums for w, two for p; interior rows: M c and K' a separately
-                {
-                  double p1 = MC(0, 1) * av[K + 1], wm1 = MC(0, 1) * cv[K + 1], wk0 = Kv * av[K], wk1 = KC(0, 1) * av[K + 1];
-                  p[0] = Mv * av[K], wv[0] = Mv * cv[K];
-#pragma unroll
-                  for (int j = 0; j < K; ++j)
+                for (int h = 0; h < C::NHALF; ++h)
+                  if (half == h)
                     {
-                      p[0]  = fma(MC(K, j), av[j], p[0]);
-                      wv[0] = fma(MC(K, j), cv[j], wv[0]);
-                      wk0   = fma(KC(K, j), av[j], wk0);
+                      // nodes h NPT .. h NPT + NPT - 1 of the segment; only the vertex node (0) reaches into the cell below
+                      constexpr int JMIN_V = 0;
+                      const int     jmin = (h == 0) ? JMIN_V : K;
+                      double        av[2 * K + 1], cv[2 * K + 1];
+#pragma unroll
+                      for (int j = 0; j < 2 * K + 1; ++j)
+                        if (j >= jmin)
+                          av[j] = ar[j * PA], cv[j] = cr[j * PA];
+#pragma unroll
+                      for (int ii = 0; ii < NPT; ++ii)
+                        {
+                          const int i = h * NPT + ii;
+                          if (i == 0 && NPT == K)
+                            {
+                              // vertex row: four partial sums for w, two for p (short dependency chains)
+                              double p1 = MC(0, 1) * av[K + 1], wm1 = MC(0, 1) * cv[K + 1], wk0 = Kv * av[K], wk1 = KC(0, 1) * av[K + 1];
+                              double p0 = Mv * av[K], w0 = Mv * cv[K];
+#pragma unroll
+                              for (int j = 0; j < K; ++j)
+                                {
+                                  p0  = fma(MC(K, j), av[j], p0);
+                                  w0  = fma(MC(K, j), cv[j], w0);
+                                  wk0 = fma(KC(K, j), av[j], wk0);
+                                }
+#pragma unroll
+                              for (int j = 2; j <= K; ++j)
+                                {
+                                  p1  = fma(MC(0, j), av[K + j], p1);
+                                  wm1 = fma(MC(0, j), cv[K + j], wm1);
+                                  wk1 = fma(KC(0, j), av[K + j], wk1);
+                                }
+                              p[ii] = p0 + p1, wv[ii] = (w0 + wm1) + (wk0 + wk1);
+                            }
+                          else if (i == 0)
+                            {
+                              // vertex row, few registers (enough warps are resident to hide the longer chains)
+                              double p0 = Mv * av[K], w0 = Mv * cv[K], wk0 = Kv * av[K];
+#pragma unroll
+                              for (int j = 0; j < K; ++j)
+                                {
+                                  p0  = fma(MC(K, j), av[j], p0);
+                                  w0  = fma(MC(K, j), cv[j], w0);
+                                  wk0 = fma(KC(K, j), av[j], wk0);
+                                }
+#pragma unroll
+                              for (int j = 1; j <= K; ++j)
+                                {
+                                  p0  = fma(MC(0, j), av[K + j], p0);
+                                  w0  = fma(MC(0, j), cv[K + j], w0);
+                                  wk0 = fma(KC(0, j), av[K + j], wk0);
+                                }
+                              p[ii] = p0, wv[ii] = w0 + wk0;
+                            }
+                          else
+                            {
+                              // interior rows: M c and K' a separately
+                              double wk = KC(i, 0) * av[K], pi = MC(i, 0) * av[K], wi = MC(i, 0) * cv[K];
+#pragma unroll
+                              for (int j = 1; j <= K; ++j)
+                                {
+                                  pi = fma(MC(i, j), av[K + j], pi);
+                                  wi = fma(MC(i, j), cv[K + j], wi);
+                                  wk = fma(KC(i, j), av[K + j], wk);
+                                }
+                              p[ii] = pi, wv[ii] = wi + wk;
+                            }
+                        }
                     }
-#pragma unroll
-                  for (int j = 2; j <= K; ++j)
-                    {
-                      p1  = fma(MC(0, j), av[K + j], p1);
-                      wm1 = fma(MC(0, j), cv[K + j], wm1);
-                      wk1 = fma(KC(0, j), av[K + j], wk1);
-                    }
-                  p[0] += p1, wv[0] = (wv[0] + wm1) + (wk0 + wk1);
-                }
-#pragma unroll
-                for (int i = 1; i < K; ++i)
-                  {
-                    double wk = KC(i, 0) * av[K];
-                    p[i] = MC(i, 0) * av[K], wv[i] = MC(i, 0) * cv[K];
-#pragma unroll
-                    for (int j = 1; j <= K; ++j)
-                      {
-                        p[i]  = fma(MC(i, j), av[K + j], p[i]);
-                        wv[i] = fma(MC(i, j), cv[K + j], wv[i]);
-                        wk    = fma(KC(i, j), av[K + j], wk);
-                      }
-                    wv[i] += wk;
-                  }
               }
               // -------------------------------------------------------------- linear part of the epilogue of this plane
               // the z-sums run on (A x) / sc - g with  g = rhs / sc (residual) | (rhs + ((1 + f1) x - f1 x_old) / (f2 dinv)) / sc
               // (Chebyshev); sc = the scalar factored out of the operator (see v3_apply)
               const bool owned = (NOPS > 0) && (ZL > 0) && !zpl && (P >= K * L0) && (P < K * L1);
-              double     g[K];
+              double     g[NPT];
 #pragma unroll
-              for (int i = 0; i < K; ++i)
+              for (int i = 0; i < NPT; ++i)
                 g[i] = 0.0;
               if (NOPS > 0 && owned)
                 {
                   if (MODE == V2_RESIDUAL)
                     {
 #pragma unroll
-                      for (int i = 0; i < K; ++i)
-                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i, par, a.sh_o0) + xl];
+                      for (int i = 0; i < NPT; ++i)
+                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i0 + i, par, a.sh_o0) + xl];
                     }
                   else
                     {
-                      const double *sdi = SDI + ((ZL % K) * K) * K + (xl % K);
+                      const double *sdi = SDI + ((ZL % K) * K + i0) * K + (xl % K);
 #pragma unroll
-                      for (int i = 0; i < K; ++i)
+                      for (int i = 0; i < NPT; ++i)
                         {
-                          const double x  = ub[urow(K + K * ys + i, par) + K + xl];
-                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i, par, a.sh_o0) + xl] : 0.0;
-                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i, par, a.sh_o1) + xl];
+                          const double x  = ub[urow(K + K * ys + i0 + i, par) + K + xl];
+                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i0 + i, par, a.sh_o0) + xl] : 0.0;
+                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i0 + i, par, a.sh_o1) + xl];
                           g[i]            = fma(fma(f1, x - xo, x), sdi[i * K], sc_inv * rh);
                         }
                     }
@@ -512,12 +549,12 @@ namespace spirk
 #pragma unroll
                   for (int z = 0; z < n; ++z)
 #pragma unroll
-                    for (int i = 0; i < K; ++i)
+                    for (int i = 0; i < NPT; ++i)
                       acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
                   if (NOPS > 0 && ZL > 0)
                     {
 #pragma unroll
-                      for (int i = 0; i < K; ++i)
+                      for (int i = 0; i < NPT; ++i)
                         acc[ZL][i] -= g[i];
                     }
                 }
@@ -526,11 +563,11 @@ namespace spirk
 #pragma unroll
                   for (int z = 0; z < n; ++z)
 #pragma unroll
-                    for (int i = 0; i < K; ++i)
+                    for (int i = 0; i < NPT; ++i)
                       acc[z][i] = fma(MC(z, K), wv[i], fma(KC(z, K), p[i], acc[z][i]));
                   if (Lc >= L0)
                     {
-                      const int       gx = gx0 + xl, gy = gy0 + K * ys;
+                      const int       gx = gx0 + xl, gy = gy0 + K * ys + i0; // first of the NPT nodes
                       const long long j0 = boff + gx + (long long)n1 * gy + plane * (K * Lc);
                       const bool      anyb = (gx == 0) || (gy == 0) || (Lc == 0);
                       if (MODE == V2_CHEB)
@@ -539,7 +576,7 @@ namespace spirk
 #pragma unroll
                           for (int z = 0; z < K; ++z)
 #pragma unroll
-                            for (int i = 0; i < K; ++i)
+                            for (int i = 0; i < NPT; ++i)
                               {
                                 const long long j = j0 + z * plane + i * n1;
                                 if (anyb && ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0)))
@@ -554,14 +591,14 @@ namespace spirk
                       else
                         {
                           double       *dp  = a.dst + j0;
-                          const double *sds = SDS + (xl % K);
+                          const double *sds = SDS + i0 * K + (xl % K);
                           const double  sca = (MODE == V2_APPLY) ? sc : -sc;
                           if (!anyb)
                             {
 #pragma unroll
                               for (int z = 0; z < K; ++z)
 #pragma unroll
-                                for (int i = 0; i < K; ++i)
+                                for (int i = 0; i < NPT; ++i)
                                   dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN) ? sds[(z * K + i) * K] : sca) * acc[z][i];
                             }
                           else
@@ -569,7 +606,7 @@ namespace spirk
 #pragma unroll
                               for (int z = 0; z < K; ++z)
 #pragma unroll
-                                for (int i = 0; i < K; ++i)
+                                for (int i = 0; i < NPT; ++i)
                                   {
                                     if ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0))
                                       v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1);
@@ -581,7 +618,7 @@ namespace spirk
                     }
                   // the top plane becomes the bottom plane of the next layer
 #pragma unroll
-                  for (int i = 0; i < K; ++i)
+                  for (int i = 0; i < NPT; ++i)
                     {
                       acc[0][i] = fma(MC(0, 0), wv[i], fma(KC(0, 0), p[i], acc[K][i])) - g[i];
 #pragma unroll
@@ -590,18 +627,19 @@ namespace spirk
                     }
                 }
             }
-          else if (ZL == K && Lc >= L0)
+          if ((NH > 0 ? !is_yz : true) && ZL == K && Lc >= L0)
             {
-              // helpers: Dirichlet faces x = n1-1 and y = n1-1 of the K planes of the completed layer (owned by no tile)
-              const int ht = tid - NY;
+              // helpers (all threads without helper warps): Dirichlet faces x = n1-1 and y = n1-1 of the K planes of the
+              // completed layer (owned by no tile)
+              const int ht = (NH > 0) ? tid - NY : tid, hs = (NH > 0) ? NH : NT;
               if (tx == a.ntx - 1)
                 {
                   const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
-                  for (int e = ht; e < K * oye; e += NH)
+                  for (int e = ht; e < K * oye; e += hs)
                     v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye));
                 }
               if (ty == a.nty - 1)
-                for (int e = ht; e < K * OX; e += NH)
+                for (int e = ht; e < K * OX; e += hs)
                   v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
             }
           if (C::PIPE)
@@ -720,14 +758,14 @@ namespace spirk
     return SPIRK_OK;
   }
 
-  template <int K, int TX, int TY, int MODE>
+  template <int K, int TX, int TY, int MODE, int NPT>
   int v3_launch_mode(spirk_ctx *ctx, V3Args &a)
   {
-    using C = CfgV3<K, TX, TY, MODE>;
+    using C = CfgV3<K, TX, TY, MODE, NPT>;
     static bool attr_set = false;
     if (!attr_set)
       {
-        SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
         attr_set = true;
       }
     const long long n_elems = (long long)(a.nb - 1) * a.stride + a.g.N;
@@ -762,23 +800,23 @@ namespace spirk
           grid       = cols * a.lock_nch;
         }
     }
-    k_v3<K, TX, TY, MODE><<<(unsigned int)grid, C::NT, C::smem, ctx->stream>>>(a);
+    k_v3<K, TX, TY, MODE, NPT><<<(unsigned int)grid, C::NT, C::smem, ctx->stream>>>(a);
     SPIRK_LAUNCH_CHECK(ctx);
     return SPIRK_OK;
   }
 
-  template <int K, int TX, int TY>
+  template <int K, int TX, int TY, int NPT>
   int v3_launch(spirk_ctx *ctx, V3Args &a, const V2Mode mode)
   {
     a.ntx = a.g.nc / TX, a.nty = a.g.nc / TY;
     a.W   = (long long)a.nb * a.ntx * a.nty * a.g.nc;
     if (mode == V2_APPLY)
-      return v3_launch_mode<K, TX, TY, V2_APPLY>(ctx, a);
+      return v3_launch_mode<K, TX, TY, V2_APPLY, NPT>(ctx, a);
     if (mode == V2_RESIDUAL)
-      return v3_launch_mode<K, TX, TY, V2_RESIDUAL>(ctx, a);
+      return v3_launch_mode<K, TX, TY, V2_RESIDUAL, NPT>(ctx, a);
     if (a.dinv != nullptr)
-      return v3_launch_mode<K, TX, TY, V2_CHEB>(ctx, a);
-    return v3_launch_mode<K, TX, TY, V2_CHEB_OWN>(ctx, a);
+      return v3_launch_mode<K, TX, TY, V2_CHEB, NPT>(ctx, a);
+    return v3_launch_mode<K, TX, TY, V2_CHEB_OWN, NPT>(ctx, a);
   }
 
   // returns SPIRK_ERR_UNSUPPORTED when the level / operator shape is not covered
@@ -822,7 +860,18 @@ namespace spirk
         small_below   = e ? atoi(e) : 64;
       }
     if (g.nc % 8 != 0 || g.nc < small_below)
-      return v3_launch<4, 4, 4>(ctx, a, mode);
-    return v3_launch<4, 8, 8>(ctx, a, mode);
+      return v3_launch<4, 4, 4, 4>(ctx, a, mode);
+    // nodes per y+z thread on the 8 x 8 tile: 4 = 20 warps/SM at 96 registers, 2 = 32 warps/SM at 64 registers (some
+    // spills); measured: 4 is better for the plain apply at r = 6, 2 for the fused epilogues
+    static int npt_env = -2;
+    if (npt_env == -2)
+      {
+        const char *e = getenv("SPIRK_V3_NPT"); // tuning knob
+        npt_env       = e ? atoi(e) : -1;
+      }
+    const int npt = (npt_env > 0) ? npt_env : (mode == V2_APPLY ? 4 : 2);
+    if (npt == 2)
+      return v3_launch<4, 8, 8, 2>(ctx, a, mode);
+    return v3_launch<4, 8, 8, 4>(ctx, a, mode);
   }
 } // namespace spirk
