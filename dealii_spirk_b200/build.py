@@ -35,7 +35,7 @@ def build_device(force=False, verbose_ptxas=False):
     srcs = device_sources()
     if not force and not _newer(DEVICE_LIB, srcs):
         return DEVICE_LIB
-    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+    cmd = [NVCC, "--split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
            "-ccbin", GXX, "-Xcompiler", "-fPIC,-O3", "-o", DEVICE_LIB, os.path.join(HERE, "csrc", "spirk_b200.cu"),
            "-ldl"]
     if verbose_ptxas:

@@ -49,7 +49,7 @@ namespace spirk
 {
   __host__ __device__ constexpr int v3_nops(const int mode) { return mode == V2_RESIDUAL ? 1 : (mode == V2_CHEB_OWN ? 2 : 0); }
 
-  template <int K, int TX, int TY, int MODE, int NPT = K>
+  template <int K, int TX, int TY, int MODE, int NPT = K, int NBC = 1>
   struct CfgV3
   {
     static constexpr int n = K + 1, OX = K * TX, OY = K * TY, LXS = OX + K + 1, LYS = OY + K + 1;
@@ -63,7 +63,7 @@ namespace spirk
 #ifdef SPIRK_V3_EXPERIMENT_MINB
     static constexpr int NBUF = 3;
 #else
-    static constexpr int NBUF = (NOPS == 0) ? 4 : 3; // ring depth (three / two planes in flight; 2 CTAs per SM must fit)
+    static constexpr int NBUF = (NOPS == 0 && NBC == 1) ? 4 : 3; // ring depth (three / two planes in flight; 2 CTAs per SM must fit)
 #endif
 #ifdef SPIRK_V3_EXPERIMENT_MINB
     static constexpr int NAC = 1;
@@ -76,7 +76,9 @@ namespace spirk
 #define SPIRK_V3_PIPE 0
 #endif
     static constexpr bool PIPE = (NAC == 2) && (SPIRK_V3_PIPE != 0);
-    static constexpr int SLOT = 2 * UB + NOPS * 2 * OB;
+    // coupled operators (NBC > 1 blocks, apply only): the x-phase mixes the mass sweeps of ALL blocks, so a ring slot
+    // holds the staged plane of every block
+    static constexpr int SLOT = NBC * 2 * UB + NOPS * 2 * OB;
     static constexpr int NHALF = K / NPT;          // a cell segment in y is shared by NHALF threads of NPT nodes each
     static constexpr int NY   = OX * TY * NHALF; // y+z tasks (one thread each)
     static constexpr int NXT  = LYS * TX; // x-phase tasks
@@ -88,9 +90,9 @@ namespace spirk
 #else
     static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 3 : 6);
 #endif
-    static constexpr unsigned BYTES_U = 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
+    static constexpr unsigned BYTES_U = NBC * 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
     static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
-    static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0, "tile shape");
+    static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0 && (NBC == 1 || NOPS == 0), "tile shape");
     static constexpr int ISSUER = (NH > 0) ? NY : 0; // the thread that issues the TMA copies
     static_assert(UB % 16 == 0 && OB % 16 == 0 && OY % 2 == 0 && BW <= 256 && BH <= 256, "128-byte aligned TMA boxes");
   };
@@ -136,6 +138,8 @@ namespace spirk
     // A = sc (Mz My K'x + Mz K'y Mx + K'z My Mx) with K' = Kh + cm / (3 cl) Mh, sc = cl  (cl = 0: K' = Mh / 3, sc = cm):
     // the mass term rides in the three stiffness terms, so no sweep scales its result
     double        sc[SPIRK_MAX_BLOCKS], kp[SPIRK_MAX_BLOCKS][V3_NKP];
+    double        cc[16]; // coupled operators (<= 4 blocks): coupling * h^3, row-major
+    int           coupled;
     int           ntx, nty;
     long long     W; // nb * columns * layers
     int           lock_nch, lock_len; // > 0: z-lockstep schedule (CTA = one column x one of lock_nch equal layer ranges)
@@ -189,10 +193,11 @@ namespace spirk
       }
   }
 
-  template <int K, int TX, int TY, int MODE, int NPT>
-  __global__ void __launch_bounds__(CfgV3<K, TX, TY, MODE, NPT>::NT, CfgV3<K, TX, TY, MODE, NPT>::MINB) k_v3(const __grid_constant__ V3Args a)
+  template <int K, int TX, int TY, int MODE, int NPT, int NBC>
+  __global__ void __launch_bounds__(CfgV3<K, TX, TY, MODE, NPT, NBC>::NT, CfgV3<K, TX, TY, MODE, NPT, NBC>::MINB)
+    k_v3(const __grid_constant__ V3Args a)
   {
-    using C = CfgV3<K, TX, TY, MODE, NPT>;
+    using C = CfgV3<K, TX, TY, MODE, NPT, NBC>;
     constexpr int n = C::n, OX = C::OX, OY = C::OY, LYS = C::LYS, BW = C::BW, UB = C::UB, OW = C::OW, OB = C::OB, PA = C::PA, NT = C::NT;
     constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT, NY = C::NY, NH = C::NH;
     extern __shared__ __align__(16) double sm3_raw[];
@@ -291,8 +296,14 @@ namespace spirk
               mbar_arrive_expect_tx(bar, (zpl ? 0u : C::BYTES_U) + (owned ? ((has_o0 ? 1u : 0u) + (NOPS == 2 ? 1u : 0u)) * C::BYTES_O : 0u));
               if (!zpl)
                 {
-                  tma_g2s_2d(dst, &a.tm_src, (gx0 - K + a.sh_src) & ~1, (int)((Rb + 1) >> 1), bar);
-                  tma_g2s_2d(dst + UB * 8, &a.tm_src, (n1 + gx0 - K + a.sh_src) & ~1, (int)(Rb >> 1), bar);
+#pragma unroll
+                  for (int j = 0; j < NBC; ++j)
+                    {
+                      // coupled: the plane of every block (block j starts rows_per_block * (j - b) rows away)
+                      const long long Rj = (NBC == 1) ? Rb : Rb + (long long)(j - b) * a.rows_per_block;
+                      tma_g2s_2d(dst + j * (2 * UB * 8), &a.tm_src, (gx0 - K + a.sh_src) & ~1, (int)((Rj + 1) >> 1), bar);
+                      tma_g2s_2d(dst + j * (2 * UB * 8) + UB * 8, &a.tm_src, (n1 + gx0 - K + a.sh_src) & ~1, (int)(Rj >> 1), bar);
+                    }
                 }
               if (owned)
                 {
@@ -362,44 +373,92 @@ namespace spirk
                 }
               else
                 {
-                  const double *ur = xub + urow(row, xpar) + K * seg;
-                  double        u[2 * K + 1];
+                  double am[K], ak[K], cmix[K];
 #pragma unroll
-                  for (int j = 0; j < 2 * K + 1; ++j)
-                    u[j] = ur[j];
-                  if (edge_x)
+                  for (int i = 0; i < K; ++i)
+                    cmix[i] = 0.0, am[i] = 0.0, ak[i] = 0.0;
+#pragma unroll
+                  for (int jb = 0; jb < NBC; ++jb)
                     {
-                      if (seg == 0 && tx == 0)
-                        { // x < 0 (outside) and x = 0 (Dirichlet)
+                      // coupled: block jb's staged plane (its row parity differs by the parity of the block distance)
+                      const int     pj = (NBC == 1) ? xpar : (xpar ^ (((jb - b) & 1) & (int)(a.rows_per_block & 1)));
+                      const double *ur = xub + jb * (2 * UB) + urow(row, pj) + K * seg;
+                      double        u[2 * K + 1];
 #pragma unroll
-                          for (int j = 0; j <= K; ++j)
-                            u[j] = 0.0;
+                      for (int j = 0; j < 2 * K + 1; ++j)
+                        u[j] = ur[j];
+                      if (edge_x)
+                        {
+                          if (seg == 0 && tx == 0)
+                            { // x < 0 (outside) and x = 0 (Dirichlet)
+#pragma unroll
+                              for (int j = 0; j <= K; ++j)
+                                u[j] = 0.0;
+                            }
+                          if (seg == 1 && tx == 0)
+                            u[0] = 0.0; // x = 0 seen from the second cell
+                          if (seg == TX - 1 && tx == a.ntx - 1)
+                            u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
                         }
-                      if (seg == 1 && tx == 0)
-                        u[0] = 0.0; // x = 0 seen from the second cell
-                      if (seg == TX - 1 && tx == a.ntx - 1)
-                        u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
+                      // mass sweep of this block; vertex row: two partial sums (short dependency chains)
+                      double mj[K];
+                      {
+                        double m1 = MC(0, 1) * u[K + 1];
+                        mj[0]     = Mv * u[K];
+#pragma unroll
+                        for (int j = 0; j < K; ++j)
+                          mj[0] = fma(MC(K, j), u[j], mj[0]);
+#pragma unroll
+                        for (int j = 2; j <= K; ++j)
+                          m1 = fma(MC(0, j), u[K + j], m1);
+                        mj[0] += m1;
+                      }
+#pragma unroll
+                      for (int i = 1; i < K; ++i)
+                        {
+                          mj[i] = MC(i, 0) * u[K];
+#pragma unroll
+                          for (int j = 1; j <= K; ++j)
+                            mj[i] = fma(MC(i, j), u[K + j], mj[i]);
+                        }
+                      if (NBC > 1)
+                        {
+                          const double cbj = a.cc[b * NBC + jb];
+#pragma unroll
+                          for (int i = 0; i < K; ++i)
+                            cmix[i] = fma(cbj, mj[i], cmix[i]);
+                        }
+                      if (NBC == 1 || jb == b)
+                        {
+                          // stiffness sweep (K' for plain operators) of the block this CTA produces
+#pragma unroll
+                          for (int i = 0; i < K; ++i)
+                            am[i] = mj[i];
+                          double k1 = KC(0, 1) * u[K + 1];
+                          ak[0]     = Kv * u[K];
+#pragma unroll
+                          for (int j = 0; j < K; ++j)
+                            ak[0] = fma(KC(K, j), u[j], ak[0]);
+#pragma unroll
+                          for (int j = 2; j <= K; ++j)
+                            k1 = fma(KC(0, j), u[K + j], k1);
+                          ak[0] += k1;
+#pragma unroll
+                          for (int i = 1; i < K; ++i)
+                            {
+                              ak[i] = KC(i, 0) * u[K];
+#pragma unroll
+                              for (int j = 1; j <= K; ++j)
+                                ak[i] = fma(KC(i, j), u[K + j], ak[i]);
+                            }
+                        }
                     }
-                  // vertex row: two partial sums each (short dependency chains)
-                  double am[K], ak[K];
-                  {
-                    double m1 = MC(0, 1) * u[K + 1], k1 = KC(0, 1) * u[K + 1];
-                    am[0] = Mv * u[K], ak[0] = Kv * u[K];
-#pragma unroll
-                    for (int j = 0; j < K; ++j)
-                      am[0] = fma(MC(K, j), u[j], am[0]), ak[0] = fma(KC(K, j), u[j], ak[0]);
-#pragma unroll
-                    for (int j = 2; j <= K; ++j)
-                      m1 = fma(MC(0, j), u[K + j], m1), k1 = fma(KC(0, j), u[K + j], k1);
-                    am[0] += m1, ak[0] += k1;
-                  }
-#pragma unroll
-                  for (int i = 1; i < K; ++i)
+                  if (NBC > 1)
                     {
-                      am[i] = MC(i, 0) * u[K], ak[i] = KC(i, 0) * u[K];
+                      // dst_b = cl_b K u_b + M sum_j C_bj u_j: a = cl Mx u_b, c = cl Kx u_b + sum_j C_bj Mx u_j
 #pragma unroll
-                      for (int j = 1; j <= K; ++j)
-                        am[i] = fma(MC(i, j), u[K + j], am[i]), ak[i] = fma(KC(i, j), u[K + j], ak[i]);
+                      for (int i = 0; i < K; ++i)
+                        ak[i] = fma(cl, ak[i], cmix[i]), am[i] *= cl;
                     }
 #pragma unroll
                   for (int i = 0; i < K; ++i)
@@ -758,14 +817,14 @@ namespace spirk
     return SPIRK_OK;
   }
 
-  template <int K, int TX, int TY, int MODE, int NPT>
+  template <int K, int TX, int TY, int MODE, int NPT, int NBC = 1>
   int v3_launch_mode(spirk_ctx *ctx, V3Args &a)
   {
-    using C = CfgV3<K, TX, TY, MODE, NPT>;
+    using C = CfgV3<K, TX, TY, MODE, NPT, NBC>;
     static bool attr_set = false;
     if (!attr_set)
       {
-        SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE, NPT, NBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
         attr_set = true;
       }
     const long long n_elems = (long long)(a.nb - 1) * a.stride + a.g.N;
@@ -800,7 +859,7 @@ namespace spirk
           grid       = cols * a.lock_nch;
         }
     }
-    k_v3<K, TX, TY, MODE, NPT><<<(unsigned int)grid, C::NT, C::smem, ctx->stream>>>(a);
+    k_v3<K, TX, TY, MODE, NPT, NBC><<<(unsigned int)grid, C::NT, C::smem, ctx->stream>>>(a);
     SPIRK_LAUNCH_CHECK(ctx);
     return SPIRK_OK;
   }
@@ -810,6 +869,11 @@ namespace spirk
   {
     a.ntx = a.g.nc / TX, a.nty = a.g.nc / TY;
     a.W   = (long long)a.nb * a.ntx * a.nty * a.g.nc;
+    if (mode == V2_APPLY && a.coupled)
+      {
+        // coupled pair of blocks (IRK q = 2 system matrix, complex pair)
+        return v3_launch_mode<K, TX, TY, V2_APPLY, K, 2>(ctx, a);
+      }
     if (mode == V2_APPLY)
       return v3_launch_mode<K, TX, TY, V2_APPLY, NPT>(ctx, a);
     if (mode == V2_RESIDUAL)
@@ -824,12 +888,15 @@ namespace spirk
                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
                       const double *f2)
   {
-    if (g.dim != 3 || g.k != 4 || op->kind != SPIRK_OP_REAL || g.nc % 4 != 0 || g.nc < 8)
+    const bool coupled = (op->kind == SPIRK_OP_COUPLED);
+    if (g.dim != 3 || g.k != 4 || g.nc % 4 != 0 || g.nc < 8)
       return SPIRK_ERR_UNSUPPORTED;
+    if (coupled && (mode != V2_APPLY || op->nb != 2))
+      return SPIRK_ERR_UNSUPPORTED; // coupled blocks: plain apply of a pair (the planes of both blocks are staged)
     if (op->nb > 1 && stride % g.n1 != 0)
       return SPIRK_ERR_UNSUPPORTED; // the blocks must continue the row sequence of block 0 (one tensor map)
     V3Args a;
-    a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1;
+    a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1, a.coupled = coupled ? 1 : 0;
     a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = dinv;
     const double hd = g.h * g.h * g.h, hl = g.h;
     constexpr int K = 4, n = K + 1;
@@ -837,19 +904,23 @@ namespace spirk
     fe_host_sym(K, Ms, Ks);
     for (int b = 0; b < op->nb; ++b)
       {
-        a.cm[b] = op->mass[b] * hd, a.cl[b] = op->laplace[b] * hl;
+        a.cm[b] = coupled ? 0.0 : op->mass[b] * hd, a.cl[b] = op->laplace[b] * hl;
         a.f1[b] = f1 ? f1[b] : 0.0, a.f2[b] = f2 ? f2[b] : 0.0;
         if (mode >= V2_CHEB && dinv == nullptr && a.f2[b] == 0.0)
           return SPIRK_ERR_UNSUPPORTED; // the folded Chebyshev epilogue divides by f2
-        if (a.cm[b] == 0.0 && a.cl[b] == 0.0)
+        if (!coupled && a.cm[b] == 0.0 && a.cl[b] == 0.0)
           return SPIRK_ERR_UNSUPPORTED; // the zero operator has no scalar to factor out
-        const bool   lap   = (a.cl[b] != 0.0);
-        const double gamma = lap ? a.cm[b] / (3.0 * a.cl[b]) : 0.0;
-        a.sc[b]            = lap ? a.cl[b] : a.cm[b];
+        // coupled: dst_b = cl_b K u_b + M sum_j C_bj u_j with the plain matrices, nothing factored out
+        const bool   lap   = coupled || (a.cl[b] != 0.0);
+        const double gamma = (lap && !coupled) ? a.cm[b] / (3.0 * a.cl[b]) : 0.0;
+        a.sc[b]            = coupled ? 1.0 : (lap ? a.cl[b] : a.cm[b]);
         for (int i = 0; i < n; ++i)
           for (int j = 0; j < n; ++j)
             a.kp[b][v3_cidx<K>(i, j)] = lap ? Ks[i * n + j] + gamma * Ms[i * n + j] : Ms[i * n + j] / 3.0;
         a.kp[b][V3_NKP - 1] = a.kp[b][v3_cidx<K>(K, K)] + a.kp[b][v3_cidx<K>(0, 0)];
+        if (coupled)
+          for (int j = 0; j < op->nb; ++j)
+            a.cc[b * op->nb + j] = op->coupling[b * op->nb + j] * hd;
       }
     // 8 x 8-cell tiles (37/32 halo) on large levels; 4 x 4-cell tiles (21/16 halo, 4 x the columns) keep all SMs busy on
     // the coarser multigrid levels
