@@ -116,6 +116,8 @@ _SIGS = {
     "spirk_comm_xbuf_destroy": [C.c_void_p, C.c_void_p],
     "spirk_mix_peer": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, dp,
                        C.c_int, C.c_double],
+    "spirk_mix_peer_a2a": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, dp,
+                           C.c_int, C.c_double],
 }
 # every symbol include/spirk_b200.h declares (tests check the library exports all of them)
 ALL_SYMBOLS = sorted(list(_SIGS) + ["spirk_backend", "spirk_last_error", "spirk_ctx_launch_count",

@@ -342,6 +342,47 @@ namespace spirk
     }
   }
 
+  // fused all-to-all + stage mixing over NVLink peer memory: this rank contracts ITS chunk [e0, e1) of every stage
+  // block (inputs read from the owners' exchange buffers) for ALL q outputs and writes each output chunk straight
+  // into the owner's result region: 2 (R-1)/R n doubles cross NVLink per rank and mixing instead of (R-1) m n
+  // for the gather formulation (k_mix_peer) - the reduce-scatter / all-gather split of the contraction
+  struct PeerPtrsRW
+  {
+    double *p[SPIRK_MAX_BLOCKS];
+  };
+  template <int Q>
+  __global__ void k_mix_a2a(const int m, const PeerPtrsRW peers, const long long n, const long long out_off, const long long e0,
+                            const long long e1, const MixMatrix T)
+  {
+    for (long long e = e0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; e < e1; e += (long long)gridDim.x * blockDim.x)
+      {
+        double in[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j)
+          in[j] = peers.p[j / m][(long long)(j % m) * n + e];
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+          {
+            double t = 0.0;
+#pragma unroll
+            for (int j = 0; j < Q; ++j)
+              t = fma(T.T[i * Q + j], in[j], t);
+            peers.p[i / m][out_off + (long long)(i % m) * n + e] = t;
+          }
+      }
+  }
+  // dst_i = [dst_i +] out_i (local result region -> destination blocks)
+  __global__ void k_mix_finish(const int m, double *dst, const long long ds, const double *__restrict__ out, const long long n,
+                               const int add)
+  {
+    SPIRK_GRID_STRIDE(e, n * m)
+    {
+      const int       i = e / n;
+      const long long k = e - i * n;
+      dst[i * ds + k]   = add ? dst[i * ds + k] + out[e] : out[e];
+    }
+  }
+
   // =========================================================================================
   // problem pieces
   // =========================================================================================

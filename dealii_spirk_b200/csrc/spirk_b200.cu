@@ -914,8 +914,9 @@ int spirk_comm_xbuf_create(spirk_ctx *ctx, spirk_comm *c, long long n, spirk_xbu
   spirk_xbuf *x = new spirk_xbuf();
   x->n = n, x->rank = c->rank, x->n_ranks = c->n_ranks;
   x->peer.assign(c->n_ranks, nullptr);
-  SPIRK_CUDA(cudaMalloc(&x->local, (size_t)n * sizeof(double)));
-  SPIRK_CUDA(cudaMemsetAsync(x->local, 0, (size_t)n * sizeof(double), ctx->stream));
+  // [0, n): this rank's published blocks; [n, 2n): result region the other ranks write into (spirk_mix_peer_a2a)
+  SPIRK_CUDA(cudaMalloc(&x->local, (size_t)2 * n * sizeof(double)));
+  SPIRK_CUDA(cudaMemsetAsync(x->local, 0, (size_t)2 * n * sizeof(double), ctx->stream));
   SPIRK_CUDA(cudaMalloc(&x->d_sync, sizeof(double)));
   SPIRK_CUDA(cudaMemsetAsync(x->d_sync, 0, sizeof(double), ctx->stream));
   x->peer[c->rank] = x->local;
@@ -989,6 +990,41 @@ int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, 
   // ... and every rank has finished reading before a buffer may be overwritten
   if (c->n_ranks > 1)
     SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  return SPIRK_OK;
+}
+
+int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, double *dst, long long ds, long long n,
+                       const double *T, int add, double cutoff)
+{
+  const int q = c->n_ranks * m;
+  if (m < 1 || q > SPIRK_MAX_BLOCKS || (long long)m * n > x->n)
+    return set_error(SPIRK_ERR_INVALID, "mix_peer_a2a: block counts / buffer size");
+  MixMatrix M;
+  for (int i = 0; i < q; ++i)
+    for (int j = 0; j < q; ++j)
+      M.T[i * q + j] = (std::fabs(T[i * q + j]) > cutoff) ? T[i * q + j] : 0.0;
+  PeerPtrsRW pp;
+  for (int r = 0; r < c->n_ranks; ++r)
+    pp.p[r] = x->peer[r];
+  // this rank's chunk of every block
+  const long long e0 = n * c->rank / c->n_ranks, e1 = n * (c->rank + 1) / c->n_ranks;
+  // stream-ordered rank barrier: every rank has published its blocks (and is done with the previous results)
+  if (c->n_ranks > 1)
+    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  const int grid = grid_for(ctx, e1 - e0, 256);
+#define MIXA_CASE(Q) \
+  case Q: k_mix_a2a<Q><<<grid, 256, 0, ctx->stream>>>(m, pp, n, x->n, e0, e1, M); break;
+  switch (q)
+    {
+      MIXA_CASE(1) MIXA_CASE(2) MIXA_CASE(3) MIXA_CASE(4) MIXA_CASE(5) MIXA_CASE(6) MIXA_CASE(7) MIXA_CASE(8)
+      MIXA_CASE(9) MIXA_CASE(10) MIXA_CASE(11) MIXA_CASE(12) MIXA_CASE(13) MIXA_CASE(14) MIXA_CASE(15) MIXA_CASE(16)
+    }
+  SPIRK_LAUNCH_CHECK(ctx);
+  // ... and every rank's result chunks have landed here
+  if (c->n_ranks > 1)
+    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  k_mix_finish<<<grid_for(ctx, n * m, 256), 256, 0, ctx->stream>>>(m, dst, ds, x->local + x->n, n, add);
+  SPIRK_LAUNCH_CHECK(ctx);
   return SPIRK_OK;
 }
 

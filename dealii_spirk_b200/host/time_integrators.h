@@ -376,6 +376,17 @@ namespace spirk_host
             // shared-memory variant, main.cc:1506-1533); no gathered copy is written
             const long long n = src.block_size();
             SPIRK_CHECK(spirk_vec_copy(src.ctx(), spirk_comm_xbuf_local(xbuf), src.data(), n * m_local));
+            if (xbuf_a2a)
+              {
+                // all-to-all: every rank contracts its chunk of every stage block for all outputs (full T)
+                std::vector<double> full((size_t)Tm.m() * Tm.n());
+                for (unsigned int i = 0; i < Tm.m(); ++i)
+                  for (unsigned int j = 0; j < Tm.n(); ++j)
+                    full[(size_t)i * Tm.n() + j] = Tm(i, j);
+                SPIRK_CHECK(spirk_mix_peer_a2a(src.ctx(), row.comm, xbuf, (int)m_local, dst.data(), dst.block_size(), n, full.data(),
+                                               add ? 1 : 0, cutoff));
+                return;
+              }
             std::vector<double> rows((size_t)m_local * Tm.n());
             for (unsigned int i = 0; i < m_local; ++i)
               for (unsigned int j = 0; j < Tm.n(); ++j)
@@ -396,6 +407,7 @@ namespace spirk_host
           {
             const char *e = std::getenv("SPIRK_PEER_MIX");
             xbuf_state    = 2;
+            xbuf_a2a      = !(e && std::atoi(e) == 1); // SPIRK_PEER_MIX=1: gather formulation, default: all-to-all
             if (!(e && std::atoi(e) == 0))
               {
                 const int st = spirk_comm_xbuf_create(src.ctx(), row.comm, src.block_size() * m_local, &xbuf);
@@ -414,6 +426,7 @@ namespace spirk_host
       }
       mutable spirk_xbuf *xbuf       = nullptr;
       mutable int         xbuf_state = 0; // 0: not tried, 1: peer exchange, 2: NCCL all-gather
+      mutable bool        xbuf_a2a   = true;
 
       struct SystemMatrix
       {

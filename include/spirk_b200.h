@@ -215,6 +215,12 @@ double *spirk_comm_xbuf_local(spirk_xbuf *xbuf); /* this rank's buffer (device p
  * exchange buffer may be overwritten as soon as the call returns (in stream order). */
 int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *comm, spirk_xbuf *xbuf, int q_out, int m_per_rank, double *dst,
                    long long dst_stride, long long n, const double *host_T, int add, double cutoff);
+/* The same mixing as an all-to-all (collective): host_T is the FULL q x q matrix (row-major); this rank contracts its
+ * 1/n_ranks chunk of every block for all q outputs and writes each output chunk straight into the owner's result
+ * region of the exchange buffer, then dst_i = [dst_i +] result_i for its own m_per_rank outputs.  2 (R-1)/R n
+ * doubles cross NVLink per rank instead of (R-1) m n. */
+int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *comm, spirk_xbuf *xbuf, int m_per_rank, double *dst, long long dst_stride,
+                       long long n, const double *host_T, int add, double cutoff);
 /* attach / detach (NULL) the communicator over which dot products are summed */
 int spirk_ctx_set_reduction_comm(spirk_ctx *ctx, spirk_comm *comm);
 

@@ -1076,6 +1076,13 @@ int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, 
     return e;
   return spirk_mix(ctx, qo, qi, dst, ds, all.data(), n, n, T, add, cutoff);
 }
+// all-to-all formulation: the same result; the CPU double gathers and mixes this rank's rows
+int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, double *dst, long long ds, long long n, const double *T,
+                       int add, double cutoff)
+{
+  const int q = c->n_ranks * m;
+  return spirk_mix_peer(ctx, c, x, m, m, dst, ds, n, T + (size_t)c->rank * m * q, add, cutoff);
+}
 int spirk_ctx_set_reduction_comm(spirk_ctx *, spirk_comm *c)
 {
   g_reduction_comm = c;
