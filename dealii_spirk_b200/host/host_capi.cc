@@ -4,6 +4,7 @@
 #include <cstring>
 #include <sstream>
 
+#include "gmg.h"
 #include "problem.h"
 
 using namespace spirk_host;
@@ -207,6 +208,24 @@ int spirk_host_table_text(spirk_run *run, char *buffer, int capacity)
     run->table.write_text(os);
     std::strncpy(buffer, os.str().c_str(), capacity - 1);
     buffer[capacity - 1] = 0;
+  });
+}
+
+/* gmg.cc benchmark (one refinement, one mode): fills values[8] = {dim, degree, n_procs, n_cells, n_dofs, L, n_iterations,
+ * time per CG iteration [s]} */
+int spirk_host_gmg(int dim, int device, int fe_degree, int n_refinements, int mode, int n_components, int n_repetitions,
+                   int n_procs, double *values)
+{
+  return guarded([&] {
+    if (dim != 2 && dim != 3)
+      throw Error("dim must be 2 or 3");
+    if (mode < 0 || mode > 3 || n_components < 1 || n_components > SPIRK_MAX_BLOCKS)
+      throw Error("gmg: mode must be 0..3, 1 <= n_components <= SPIRK_MAX_BLOCKS");
+    Device                dev(device);
+    GMGBenchmark::Result r = (dim == 2) ? GMGBenchmark::test<2>(dev, fe_degree, n_refinements, mode, n_components, n_repetitions, n_procs) :
+                                          GMGBenchmark::test<3>(dev, fe_degree, n_refinements, mode, n_components, n_repetitions, n_procs);
+    values[0] = r.dim, values[1] = r.degree, values[2] = r.n_procs, values[3] = (double)r.n_cells, values[4] = (double)r.n_dofs;
+    values[5] = r.L, values[6] = r.n_iterations, values[7] = r.time;
   });
 }
 }

@@ -32,9 +32,19 @@ class HostLib:
         lib.spirk_host_get_array.argtypes = [C.c_void_p, C.c_char_p, dp, C.c_int, C.POINTER(C.c_int)]
         lib.spirk_host_get_solution.argtypes = [C.c_void_p, C.c_void_p]
         lib.spirk_host_table_text.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.spirk_host_gmg.argtypes = [C.c_int] * 8 + [dp]
 
     def backend(self):
         return self.lib.spirk_host_backend().decode()
+
+    GMG_COLUMNS = ("dim", "degree", "n_procs", "n_cells", "n_dofs", "L", "n_iterations", "time")
+
+    def gmg(self, dim, degree, n_refinements, mode, n_components=8, n_repetitions=10, device=0, n_procs=1):
+        """one row of the reference's gmg.cc benchmark table (mode 0..3, gmg.cc:342-382)"""
+        v = (C.c_double * 8)()
+        self.check(self.lib.spirk_host_gmg(dim, device, degree, n_refinements, mode, n_components, n_repetitions, n_procs, v),
+                   "spirk_host_gmg")
+        return dict(zip(self.GMG_COLUMNS, list(v)))
 
     def check(self, st, what):
         if st != 0:

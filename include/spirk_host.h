@@ -53,6 +53,14 @@ int spirk_host_get_solution(spirk_run *run, double *host_solution);
 /* the ConvergenceTable as text (columns of main.cc:689-719, 3360-3368, 3387-3398) */
 int spirk_host_table_text(spirk_run *run, char *buffer, int capacity);
 
+/* The reference's gmg.cc benchmark for one refinement level and one of its four modes (gmg.cc:342-382):
+ * 0 = one component, 1 = n_components in one vector-valued system, 2 = one component per process group
+ * (n_procs groups), 3 = n_components batched.  GMG-preconditioned CG on (M + K) u = 1 to a 1e-12 reduction,
+ * one warm-up solve + n_repetitions timed solves.  values[8] = {dim, degree, n_procs, n_cells, n_dofs, L,
+ * n_iterations, seconds per CG iteration} (the table columns of gmg.cc:293-307). */
+int spirk_host_gmg(int dim, int device, int fe_degree, int n_refinements, int mode, int n_components, int n_repetitions,
+                   int n_procs, double *values);
+
 #ifdef __cplusplus
 }
 #endif

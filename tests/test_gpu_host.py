@@ -59,3 +59,9 @@ def test_manufactured_solution_full_size(gpu_host):
         assert np.all(res["outer"] <= 10)
     # r=3 -> r=4: spatial order 5 (factor 32); at r=5 the tau^7 time error (~1e-8) starts to show
     assert errs[4] < errs[3] / 16.0 and errs[5] < errs[4] / 4.0, errs
+
+
+def test_gmg_benchmark_modes(gpu_host):
+    """the reference's gmg.cc benchmark modes on the GPU: iteration counts as the oracle"""
+    hc.check_gmg_benchmark(gpu_host, 3, 4, 2, n_components=3)
+    hc.check_gmg_benchmark(gpu_host, 2, 2, 4, n_components=8)

@@ -52,3 +52,9 @@ def test_parameter_errors(cpu_host):
     with pytest.raises(capi.SpirkError):  # no complex tables for q = 10
         run = hostapi.Run(cpu_host, hc.params("complex_irk", 1, 2, 10), dim=2)
         run.setup()
+
+
+def test_gmg_benchmark_modes(cpu_host):
+    # the reference's gmg.cc benchmark (1 component / n components / n groups / batched)
+    hc.check_gmg_benchmark(cpu_host, 2, 2, 3)
+    hc.check_gmg_benchmark(cpu_host, 3, 4, 1, n_components=2)
