@@ -99,3 +99,22 @@ def test_product_library_exports_every_symbol():
         h = C.c_void_p()
         st = dev.lib.spirk_ctx_create(C.byref(h), 0)
         assert st == 2, "product library must fail loudly (SPIRK_ERR_DEVICE) without a GPU"
+
+
+def test_host_library_exports_every_symbol():
+    """include/spirk_host.h <-> libspirk_host.so (the C++ host layer linked against the CUDA library)."""
+    import re
+    import dealii_spirk_b200
+    path = dealii_spirk_b200.HOST_LIB_PATH
+    if not os.path.exists(path):
+        import __graft_entry__
+        __graft_entry__.build()
+    C.CDLL(dealii_spirk_b200.DEVICE_LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "spirk_host.h")).read()
+    declared = sorted(set(re.findall(r"\b(spirk_host_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.spirk_host_backend.restype = C.c_char_p
+    assert lib.spirk_host_backend().decode() == "cuda-sm_100a"
