@@ -42,7 +42,9 @@ namespace spirk
     V2_APPLY    = 0, // dst = A src
     V2_RESIDUAL = 1, // dst = rhs - A src
     V2_CHEB     = 2, // dst = src + f1 (src - x_old) + f2 dinv (rhs - A src)
-    V2_CHEB_OWN = 3  // the same with dinv = the operator's own inverse diagonal, computed on the fly
+    V2_CHEB_OWN = 3, // the same with dinv = the operator's own inverse diagonal, computed on the fly
+    // first two Chebyshev iterates in one pass (variant 3 only): x1 = f0 dinv src, dst = x1 + f1 x1 + f2 dinv (src - A x1)
+    V2_CHEB_FIRST = 4
   };
 
   template <int K, int TX, int TY>

@@ -91,7 +91,7 @@ namespace spirk
     static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 3 : 6);
 #endif
     static constexpr unsigned BYTES_U = NBC * 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
-    static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 2 * K * K * K + NBUF);
+    static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 3 * K * K * K + NBUF);
     static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0 && (NBC == 1 || NOPS == 0), "tile shape");
     static constexpr int ISSUER = (NH > 0) ? NY : 0; // the thread that issues the TMA copies
     static_assert(UB % 16 == 0 && OB % 16 == 0 && OY % 2 == 0 && BW <= 256 && BH <= 256, "128-byte aligned TMA boxes");
@@ -138,7 +138,8 @@ namespace spirk
     // A = sc (Mz My K'x + Mz K'y Mx + K'z My Mx) with K' = Kh + cm / (3 cl) Mh, sc = cl  (cl = 0: K' = Mh / 3, sc = cm):
     // the mass term rides in the three stiffness terms, so no sweep scales its result
     double        sc[SPIRK_MAX_BLOCKS], kp[SPIRK_MAX_BLOCKS][V3_NKP];
-    double        cc[16]; // coupled operators (<= 4 blocks): coupling * h^3, row-major
+    double        cc[16]; // coupled operators (<= 4 blocks): coupling * h^3, row-major; V2_CHEB_FIRST: f0 of the blocks
+                          // (x1 = f0 dinv src; x1 is written to the `dinv` pointer, which that mode does not read)
     int           coupled;
     int           ntx, nty;
     long long     W; // nb * columns * layers
@@ -147,6 +148,8 @@ namespace spirk
     int           sh_src, sh_o0, sh_o1; // element shift of the 16-byte aligned map base below the vector
     alignas(64) CUtensorMap tm_src, tm_o0, tm_o1; // staged nodes; operand 0 (rhs | x_old); operand 1 (rhs)
   };
+
+  static_assert(sizeof(V3Args) <= 4096, "kernel parameter space");
 
   __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
   __device__ __forceinline__ void     mbar_init(const unsigned bar, const int count)
@@ -178,13 +181,19 @@ namespace spirk
 
   // identity rows (Dirichlet nodes): A x = x
   template <int MODE>
-  __device__ __forceinline__ void v3_identity(const V3Args &a, const double f1, const double f2, const long long j)
+  __device__ __forceinline__ void v3_identity(const V3Args &a, const double f1, const double f2, const long long j, const double f0 = 0.0)
   {
     const double x = a.src[j];
     if (MODE == V2_APPLY)
       a.dst[j] = x;
     else if (MODE == V2_RESIDUAL)
       a.dst[j] = a.rhs[j] - x;
+    else if (MODE == V2_CHEB_FIRST)
+      {
+        const double x1 = f0 * x; // the inverse diagonal is 1 on Dirichlet nodes
+        const_cast<double *>(a.dinv)[j] = x1;
+        a.dst[j]        = fma(f2, x - x1, fma(f1, x1, x1));
+      }
     else
       {
         const double xo = a.x_old ? a.x_old[j] : 0.0;
@@ -202,8 +211,8 @@ namespace spirk
     constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT, NY = C::NY, NH = C::NH;
     extern __shared__ __align__(16) double sm3_raw[];
     double   *sm3  = sm3_raw + (((128u - (smem_u32(sm3_raw) & 127u)) & 127u) >> 3); // TMA boxes: 128-byte aligned
-    double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K;
-    uint64_t *BAR  = reinterpret_cast<uint64_t *>(SDI + K * K * K);
+    double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K, *SD1 = SDI + K * K * K;
+    uint64_t *BAR  = reinterpret_cast<uint64_t *>(SD1 + K * K * K);
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
     const double  Mv = c_fe[K].Mv;
 #define MC(i, j) Mh[v3_canon<K>(i, j)]
@@ -252,6 +261,8 @@ namespace spirk
         const int       gx0 = tx * OX, gy0 = ty * OY;
         const double    cm = a.cm[b], cl = a.cl[b], f1 = a.f1[b], f2 = a.f2[b], sc = a.sc[b], sc_inv = 1.0 / sc;
         const double   *kp = a.kp[b];
+        constexpr bool  CF = (MODE == V2_CHEB_FIRST);
+        const double    f0 = CF ? a.cc[b] : 0.0, kappa = CF ? (1.0 + (1.0 + f1) * f0 / f2) * sc_inv : 0.0;
         const double    Kv = kp[V3_NKP - 1];
         const long long boff = (long long)b * a.stride;
         const double   *src  = a.src + boff;
@@ -261,7 +272,7 @@ namespace spirk
         const bool      edge_x = (tx == 0) || (tx == a.ntx - 1);
 
         __syncthreads(); // the previous piece is finished with the ring, the a'/c tile and the tables
-        if (MODE == V2_CHEB_OWN && b != b_tab)
+        if ((MODE == V2_CHEB_OWN || MODE == V2_CHEB_FIRST) && b != b_tab)
           {
             // scaling by node class (position of the node inside its cell): -f2 / diag and its inverse
             for (int e = tid; e < K * K * K; e += NT)
@@ -273,9 +284,11 @@ namespace spirk
                 const double mz = cz ? Mh[cz * n + cz] : Mv, kz = cz ? Kh[cz * n + cz] : Kv0;
                 const double d  = cm * mx * my * mz + cl * (kx * my * mz + mx * ky * mz + mx * my * kz);
                 const double di = (fabs(d) > 1.0e-10) ? 1.0 / d : 1.0;
-                SDS[e] = -f2 * di * sc, SDI[e] = 1.0 / (f2 * di * sc);
+                SDS[e] = -f2 * di * sc, SDI[e] = 1.0 / (f2 * di * sc), SD1[e] = f0 * di;
               }
             b_tab = b;
+            if (CF)
+              __syncthreads(); // the x-phase of the first plane already reads the table
           }
 
         // ------------------------------------------------------------------ staging of one node plane (one thread)
@@ -399,6 +412,14 @@ namespace spirk
                             u[0] = 0.0; // x = 0 seen from the second cell
                           if (seg == TX - 1 && tx == a.ntx - 1)
                             u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
+                        }
+                      if (CF)
+                        {
+                          // first Chebyshev iterate x1 = f0 D^-1 b formed on the fly (node class = position in the cell)
+                          const double *d1 = SD1 + ((((xP % K) + K) % K) * K + (row % K)) * K;
+#pragma unroll
+                          for (int j = 0; j < 2 * K + 1; ++j)
+                            u[j] *= d1[j % K];
                         }
                       // mass sweep of this block; vertex row: two partial sums (short dependency chains)
                       double mj[K];
@@ -576,11 +597,26 @@ namespace spirk
               // -------------------------------------------------------------- linear part of the epilogue of this plane
               // the z-sums run on (A x) / sc - g with  g = rhs / sc (residual) | (rhs + ((1 + f1) x - f1 x_old) / (f2 dinv)) / sc
               // (Chebyshev); sc = the scalar factored out of the operator (see v3_apply)
-              const bool owned = (NOPS > 0) && (ZL > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+              const bool owned = (NOPS > 0 || CF) && (ZL > 0) && !zpl && (P >= K * L0) && (P < K * L1);
               double     g[NPT];
 #pragma unroll
               for (int i = 0; i < NPT; ++i)
                 g[i] = 0.0;
+              if (CF && owned)
+                {
+                  // b = src of this plane: g = kappa b; the first iterate x1 = f0 D^-1 b is stored here, plane by plane
+                  const double   *sd1 = SD1 + ((ZL % K) * K + i0) * K + (xl % K);
+                  const int       gx = gx0 + xl, gyf = gy0 + K * ys + i0;
+                  double         *d1p = const_cast<double *>(a.dinv) + boff + gx + (long long)n1 * gyf + plane * P;
+#pragma unroll
+                  for (int i = 0; i < NPT; ++i)
+                    {
+                      const double bi = ub[urow(K + K * ys + i0 + i, par) + K + xl];
+                      g[i]            = kappa * bi;
+                      if (gx != 0 && gyf + i != 0)
+                        d1p[i * n1] = sd1[i * K] * bi;
+                    }
+                }
               if (NOPS > 0 && owned)
                 {
                   if (MODE == V2_RESIDUAL)
@@ -610,7 +646,7 @@ namespace spirk
 #pragma unroll
                     for (int i = 0; i < NPT; ++i)
                       acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
-                  if (NOPS > 0 && ZL > 0)
+                  if ((NOPS > 0 || CF) && ZL > 0)
                     {
 #pragma unroll
                       for (int i = 0; i < NPT; ++i)
@@ -639,7 +675,7 @@ namespace spirk
                               {
                                 const long long j = j0 + z * plane + i * n1;
                                 if (anyb && ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0)))
-                                  v3_identity<MODE>(a, f1, f2, j);
+                                  v3_identity<MODE>(a, f1, f2, j, f0);
                                 else
                                   {
                                     const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
@@ -658,7 +694,7 @@ namespace spirk
                               for (int z = 0; z < K; ++z)
 #pragma unroll
                                 for (int i = 0; i < NPT; ++i)
-                                  dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN) ? sds[(z * K + i) * K] : sca) * acc[z][i];
+                                  dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN || CF) ? sds[(z * K + i) * K] : sca) * acc[z][i];
                             }
                           else
                             {
@@ -668,9 +704,9 @@ namespace spirk
                                 for (int i = 0; i < NPT; ++i)
                                   {
                                     if ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0))
-                                      v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1);
+                                      v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1, f0);
                                     else
-                                      dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN) ? sds[(z * K + i) * K] : sca) * acc[z][i];
+                                      dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN || CF) ? sds[(z * K + i) * K] : sca) * acc[z][i];
                                   }
                             }
                         }
@@ -695,11 +731,11 @@ namespace spirk
                 {
                   const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
                   for (int e = ht; e < K * oye; e += hs)
-                    v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye));
+                    v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye), f0);
                 }
               if (ty == a.nty - 1)
                 for (int e = ht; e < K * OX; e += hs)
-                  v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX));
+                  v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX), f0);
             }
           if (C::PIPE)
             {
@@ -739,7 +775,7 @@ namespace spirk
           {
             const int oxe = OX + (tx == a.ntx - 1 ? 1 : 0), oye = OY + (ty == a.nty - 1 ? 1 : 0);
             for (int e = tid; e < oxe * oye; e += NT)
-              v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % oxe) + (long long)n1 * (gy0 + e / oxe) + plane * (n1 - 1));
+              v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % oxe) + (long long)n1 * (gy0 + e / oxe) + plane * (n1 - 1), f0);
           }
       }
 #undef MC
@@ -878,6 +914,8 @@ namespace spirk
       return v3_launch_mode<K, TX, TY, V2_APPLY, NPT>(ctx, a);
     if (mode == V2_RESIDUAL)
       return v3_launch_mode<K, TX, TY, V2_RESIDUAL, NPT>(ctx, a);
+    if (mode == V2_CHEB_FIRST)
+      return v3_launch_mode<K, TX, TY, V2_CHEB_FIRST, NPT>(ctx, a);
     if (a.dinv != nullptr)
       return v3_launch_mode<K, TX, TY, V2_CHEB, NPT>(ctx, a);
     return v3_launch_mode<K, TX, TY, V2_CHEB_OWN, NPT>(ctx, a);
@@ -886,7 +924,7 @@ namespace spirk
   // returns SPIRK_ERR_UNSUPPORTED when the level / operator shape is not covered
   inline int v3_apply(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, V2Mode mode, double *dst, const double *src,
                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
-                      const double *f2)
+                      const double *f2, const double *f0 = nullptr, double *dst1 = nullptr)
   {
     const bool coupled = (op->kind == SPIRK_OP_COUPLED);
     if (g.dim != 3 || g.k != 4 || g.nc % 4 != 0 || g.nc < 8)
@@ -897,7 +935,9 @@ namespace spirk
       return SPIRK_ERR_UNSUPPORTED; // the blocks must continue the row sequence of block 0 (one tensor map)
     V3Args a;
     a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1, a.coupled = coupled ? 1 : 0;
-    a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = dinv;
+    a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = (mode == V2_CHEB_FIRST) ? dst1 : dinv;
+    if (mode == V2_CHEB_FIRST && (coupled || f0 == nullptr || dst1 == nullptr || dst1 == dst || dst1 == src))
+      return SPIRK_ERR_UNSUPPORTED;
     const double hd = g.h * g.h * g.h, hl = g.h;
     constexpr int K = 4, n = K + 1;
     double        Ms[n * n], Ks[n * n];
@@ -906,6 +946,8 @@ namespace spirk
       {
         a.cm[b] = coupled ? 0.0 : op->mass[b] * hd, a.cl[b] = op->laplace[b] * hl;
         a.f1[b] = f1 ? f1[b] : 0.0, a.f2[b] = f2 ? f2[b] : 0.0;
+        if (mode == V2_CHEB_FIRST)
+          a.cc[b] = f0[b];
         if (mode >= V2_CHEB && dinv == nullptr && a.f2[b] == 0.0)
           return SPIRK_ERR_UNSUPPORTED; // the folded Chebyshev epilogue divides by f2
         if (!coupled && a.cm[b] == 0.0 && a.cl[b] == 0.0)

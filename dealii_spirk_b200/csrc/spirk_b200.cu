@@ -511,6 +511,33 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
   return SPIRK_OK;
 }
 
+int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                        long long stride, const double *f0, const double *f1, const double *f2)
+{
+  if (int e = check_level(lvl))
+    return e;
+  if (int e = check_op(op))
+    return e;
+  if (op->kind != SPIRK_OP_REAL)
+    return set_error(SPIRK_ERR_INVALID, "op_cheb_first: needs a REAL operator (its own inverse diagonal)");
+  if (x1 == x2 || x1 == rhs || x2 == rhs)
+    return set_error(SPIRK_ERR_INVALID, "op_cheb_first: x1, x2 and rhs must be distinct");
+  const Geo g = make_geo(lvl);
+  if (ctx->opt_apply_variant == 0)
+    {
+      int st = v3_apply(ctx, g, op, V2_CHEB_FIRST, x2, rhs, nullptr, nullptr, nullptr, stride, f1, f2, f0, x1);
+      if (st != SPIRK_ERR_UNSUPPORTED)
+        return st;
+    }
+  // general path: D^-1 into x2, x1 = f0 D^-1 rhs, then the ordinary Chebyshev step with x_old = 0
+  for (int b = 0; b < op->nb; ++b)
+    if (int e = spirk_op_inverse_diagonal(ctx, lvl, x2 + (size_t)b * stride, op->mass[b], op->laplace[b]))
+      return e;
+  if (int e = spirk_vec_scale_pointwise(ctx, op->nb, g.N, x1, x2, rhs, stride, f0))
+    return e;
+  return spirk_op_cheb_step(ctx, lvl, op, x2, x1, nullptr, rhs, nullptr, stride, f1, f2);
+}
+
 int spirk_op_inverse_diagonal(spirk_ctx *ctx, const spirk_level *lvl, double *diag, double mass, double laplace)
 {
   if (int e = check_level(lvl))

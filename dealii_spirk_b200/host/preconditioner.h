@@ -6,6 +6,7 @@
 // PreconditionerAMG (Trilinos ML on an assembled matrix, ref preconditioner.h:176-215) is out of
 // scope.
 #pragma once
+#include <cstdlib>
 #include <functional>
 #include <memory>
 
@@ -182,10 +183,10 @@ namespace spirk_host
         std::vector<double> f(nb), f1(nb), f2(nb);
         for (int i = 0; i < nb; ++i)
           f[i] = 1.0 / L.theta[i];
-        SPIRK_CHECK(spirk_vec_scale_pointwise(dev->ctx(), nb, L.n, x.data(), L.dinv.data(), b.data(), L.n, f.data()));
-        if (degree < 2)
-          return;
-        const spirk_opdesc  op = opdesc(l);
+        const spirk_opdesc op = opdesc(l);
+        bool own_dinv = op.kind == SPIRK_OP_REAL && (int)L.dinv_mass.size() == nb;
+        for (int i = 0; own_dinv && i < nb; ++i)
+          own_dinv = L.dinv_mass[i] == op.mass[i] && L.dinv_laplace[i] == op.laplace[i];
         std::vector<double> rhok(nb), sigma(nb);
         bool                any = false;
         for (int i = 0; i < nb; ++i)
@@ -193,11 +194,12 @@ namespace spirk_host
             rhok[i] = L.delta[i] / L.theta[i], sigma[i] = L.theta[i] / L.delta[i];
             any = any || std::fabs(L.delta[i]) >= 1e-40;
           }
-        if (!any)
+        // iterations 0 and 1 in one pass over b when the smoother's diagonal is the level operator's own
+        const bool fuse_first = own_dinv && degree >= 2 && any && fuse_first_iterations();
+        if (!fuse_first)
+          SPIRK_CHECK(spirk_vec_scale_pointwise(dev->ctx(), nb, L.n, x.data(), L.dinv.data(), b.data(), L.n, f.data()));
+        if (degree < 2 || !any)
           return;
-        bool own_dinv = op.kind == SPIRK_OP_REAL && (int)L.dinv_mass.size() == nb;
-        for (int i = 0; own_dinv && i < nb; ++i)
-          own_dinv = L.dinv_mass[i] == op.mass[i] && L.dinv_laplace[i] == op.laplace[i];
         double *cur = x.data(), *old = L.tmp.data();
         for (unsigned int k = 0; k < degree - 1; ++k)
           {
@@ -208,12 +210,26 @@ namespace spirk_host
                 rhok[i] = rhokp;
               }
             // x_new overwrites the x_old buffer (deal.II swaps solution / solution_old)
-            SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
-                                           own_dinv ? nullptr : L.dinv.data(), L.n, f1.data(), f2.data()));
+            if (k == 0 && fuse_first)
+              SPIRK_CHECK(spirk_op_cheb_first(dev->ctx(), &L.level, &op, cur, old, b.data(), L.n, f.data(), f1.data(), f2.data()));
+            else
+              SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
+                                             own_dinv ? nullptr : L.dinv.data(), L.n, f1.data(), f2.data()));
             std::swap(cur, old);
           }
         if (cur != x.data()) // odd number of steps: result sits in the tmp buffer
           SPIRK_CHECK(spirk_vec_copy(dev->ctx(), x.data(), cur, L.n * nb));
+      }
+
+      static bool fuse_first_iterations()
+      {
+        static int v = -1;
+        if (v < 0)
+          {
+            const char *e = std::getenv("SPIRK_FUSE_CHEB_FIRST"); // 0: scale + Chebyshev step as two kernels
+            v             = (e && std::atoi(e) == 0) ? 0 : 1;
+          }
+        return v == 1;
       }
 
       void coarse_solve()

@@ -574,6 +574,23 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
   return SPIRK_OK;
 }
 
+// first two Chebyshev iterates from a zero start: x1 = f0 dinv rhs, x2 = x1 + f1 x1 + f2 dinv (rhs - A x1)
+int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                        long long stride, const double *f0, const double *f1, const double *f2)
+{
+  if (op->kind != SPIRK_OP_REAL)
+    return fail(SPIRK_ERR_INVALID, "cheb_first: needs a REAL operator");
+  const long long N = Geo(lvl).N;
+  for (int b = 0; b < op->nb; ++b)
+    {
+      if (int e = spirk_op_inverse_diagonal(ctx, lvl, x2 + b * stride, op->mass[b], op->laplace[b]))
+        return e;
+      for (long long i = 0; i < N; ++i)
+        x1[b * stride + i] = f0[b] * x2[b * stride + i] * rhs[b * stride + i];
+    }
+  return spirk_op_cheb_step(ctx, lvl, op, x2, x1, nullptr, rhs, nullptr, stride, f1, f2);
+}
+
 int spirk_op_inverse_diagonal(spirk_ctx *, const spirk_level *lvl, double *diag, double mass, double laplace)
 {
   if (int e = check_level(lvl))

@@ -108,6 +108,17 @@ def check_residual_and_cheb(dev, dim, k, r, nb=2):
         new = ctx.download(dnew, x.shape)
         ref = x + f1[bc] * (x - xo) + f2[bc] * dinv * (b - Ax)
         assert relerr(new, ref) < RTOL
+        # iterations 0 and 1 from a zero start in one pass (spirk_op_cheb_first)
+        f0 = np.array([0.7, 0.6, 0.65, 0.75][:nb])
+        pf0, _c = capi.darr(f0)
+        dx1, dx2 = ctx.alloc(x.size), ctx.alloc(x.size)
+        bb = block_input(olv, nb, 6, False)  # boundary values of the right-hand side take part (identity rows)
+        dbb = ctx.upload(bb)
+        ctx.call("spirk_op_cheb_first", C.byref(lvl), C.byref(op), dx1, dx2, dbb, olv.N, pf0, pf1, pf2)
+        x1 = f0[bc] * dinv * bb
+        x2 = x1 + f1[bc] * x1 + f2[bc] * dinv * (bb - olv.apply(x1, mass, lap))
+        assert relerr(ctx.download(dx1, x.shape), x1) < RTOL
+        assert relerr(ctx.download(dx2, x.shape), x2) < RTOL
         # x_new aliasing x_old (how the smoother calls it)
         ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dxo, dx, dxo, db, None, olv.N, pf1, pf2)
         assert relerr(ctx.download(dxo, x.shape), ref) < RTOL
