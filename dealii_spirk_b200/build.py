@@ -32,15 +32,31 @@ def device_sources():
 
 
 def build_device(force=False, verbose_ptxas=False):
+    """One object per translation unit (the main unit + one unit per mode of the plane-streaming cell operator,
+    csrc/v3_mode*.cu), compiled side by side, each single-threaded: nvcc --split-compile gave a different register
+    allocation of the hot kernels from build to build (see profiles/README.md), separate units are deterministic."""
     srcs = device_sources()
     if not force and not _newer(DEVICE_LIB, srcs):
         return DEVICE_LIB
-    cmd = [NVCC, "--split-compile", "0", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-           "-ccbin", GXX, "-Xcompiler", "-fPIC,-O3", "-o", DEVICE_LIB, os.path.join(HERE, "csrc", "spirk_b200.cu"),
-           "-ldl"]
+    csrc = os.path.join(HERE, "csrc")
+    units = ["spirk_b200.cu"] + sorted(f for f in os.listdir(csrc) if f.startswith("v3_mode") and f.endswith(".cu"))
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    base = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", GXX,
+            "-Xcompiler", "-fPIC,-O3"]
     if verbose_ptxas:
-        cmd.insert(1, "-Xptxas=-v")
-    _run(cmd)
+        base.insert(1, "-Xptxas=-v")
+    procs, objs = [], []
+    for u in units:
+        obj = os.path.join(objdir, u[:-3] + ".o")
+        objs.append(obj)
+        cmd = base + ["-c", "-o", obj, os.path.join(csrc, u)]
+        print("+", " ".join(cmd), flush=True)
+        procs.append((u, subprocess.Popen(cmd)))
+    for u, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, u)
+    _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", GXX, "-o", DEVICE_LIB] + objs + ["-ldl"])
     return DEVICE_LIB
 
 

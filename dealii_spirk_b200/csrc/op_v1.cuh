@@ -19,7 +19,9 @@
 
 namespace spirk
 {
-  __constant__ FeConst c_fe[SPIRK_MAX_DEGREE + 1];
+  // one copy per translation unit (the plane-streaming kernels are compiled in separate units, see build.py);
+  // upload_fe_constants() fills all of them
+  static __constant__ FeConst c_fe[SPIRK_MAX_DEGREE + 1];
 
   __device__ __forceinline__ bool on_bdry(const int i, const int n1) { return i == 0 || i == n1 - 1; }
 
@@ -51,7 +53,7 @@ namespace spirk
 
   // dst_b = boundary ? src_b : 0   (replaces cell_loop's zero_dst + the constrained-DoF identity,
   // operator.h:301-309)
-  __global__ void k_init_dst(const Geo g, const int nb, double *__restrict__ dst, const double *__restrict__ src,
+  static __global__ void k_init_dst(const Geo g, const int nb, double *__restrict__ dst, const double *__restrict__ src,
                              const long long stride)
   {
     const long long total = g.N * nb;
@@ -307,7 +309,7 @@ namespace spirk
 
   // ---- unfused epilogues ------------------------------------------------------------------
   // dst = rhs - t
-  __global__ void k_residual_epilogue(const long long N, const int nb, double *__restrict__ dst, const double *__restrict__ rhs,
+  static __global__ void k_residual_epilogue(const long long N, const int nb, double *__restrict__ dst, const double *__restrict__ rhs,
                                       const double *__restrict__ t, const long long stride, const long long tstride)
   {
     const long long total = N * nb;
@@ -325,7 +327,7 @@ namespace spirk
   };
 
   // x_new = (1 + f1) x - f1 x_old + f2 dinv (rhs - t)      (deal.II VectorUpdater)
-  __global__ void k_cheb_epilogue(const long long N, const int nb, double *x_new, const double *__restrict__ x,
+  static __global__ void k_cheb_epilogue(const long long N, const int nb, double *x_new, const double *__restrict__ x,
                                   const double *x_old, const double *__restrict__ rhs, const double *__restrict__ dinv,
                                   const double *__restrict__ t, const long long stride, const long long tstride,
                                   const ChebFactors f, const long long dstride)

@@ -900,6 +900,26 @@ namespace spirk
     return SPIRK_OK;
   }
 
+#ifndef SPIRK_V3_INSTANTIATE
+  // the kernels are instantiated in csrc/v3_mode*.cu (one translation unit per mode)
+#define SPIRK_V3_EXTERN(MODE)                                                                \
+  extern template int v3_launch_mode<4, 8, 8, MODE, 4, 1>(spirk_ctx *, V3Args &);           \
+  extern template int v3_launch_mode<4, 8, 8, MODE, 2, 1>(spirk_ctx *, V3Args &);           \
+  extern template int v3_launch_mode<4, 4, 4, MODE, 4, 1>(spirk_ctx *, V3Args &);
+  SPIRK_V3_EXTERN(V2_APPLY)
+  SPIRK_V3_EXTERN(V2_RESIDUAL)
+  SPIRK_V3_EXTERN(V2_CHEB)
+  SPIRK_V3_EXTERN(V2_CHEB_OWN)
+  SPIRK_V3_EXTERN(V2_CHEB_FIRST)
+  extern template int v3_launch_mode<4, 8, 8, V2_APPLY, 4, 2>(spirk_ctx *, V3Args &);
+  extern template int v3_launch_mode<4, 4, 4, V2_APPLY, 4, 2>(spirk_ctx *, V3Args &);
+#undef SPIRK_V3_EXTERN
+  int v3_upload_constants_mode0(const FeConst *all);
+  int v3_upload_constants_mode1(const FeConst *all);
+  int v3_upload_constants_mode2(const FeConst *all);
+  int v3_upload_constants_mode3(const FeConst *all);
+  int v3_upload_constants_mode4(const FeConst *all);
+
   template <int K, int TX, int TY, int NPT>
   int v3_launch(spirk_ctx *ctx, V3Args &a, const V2Mode mode)
   {
@@ -970,7 +990,7 @@ namespace spirk
     if (small_below < 0)
       {
         const char *e = getenv("SPIRK_V3_SMALL_BELOW"); // tuning knob: levels with fewer cells per direction use 4 x 4 tiles
-        small_below   = e ? atoi(e) : 64;
+        small_below   = e ? atoi(e) : 32; // measured (IRK q=2 step, r=6): 64 -> 48.2 ms, 32 -> 46.7 ms, 16 -> 47.0 ms
       }
     if (g.nc % 8 != 0 || g.nc < small_below)
       return v3_launch<4, 4, 4, 4>(ctx, a, mode);
@@ -987,4 +1007,5 @@ namespace spirk
       return v3_launch<4, 8, 8, 2>(ctx, a, mode);
     return v3_launch<4, 8, 8, 4>(ctx, a, mode);
   }
+#endif // SPIRK_V3_INSTANTIATE
 } // namespace spirk

@@ -63,6 +63,17 @@ namespace spirk
         all[k].Mv = all[k].Mh[k * n + k] + all[k].Mh[0], all[k].Kv = all[k].Kh[k * n + k] + all[k].Kh[0];
       }
     SPIRK_CUDA(cudaMemcpyToSymbol(c_fe, all, sizeof(all)));
+    // the copies of the separately compiled plane-streaming kernels
+    if (int e = v3_upload_constants_mode0(all))
+      return e;
+    if (int e = v3_upload_constants_mode1(all))
+      return e;
+    if (int e = v3_upload_constants_mode2(all))
+      return e;
+    if (int e = v3_upload_constants_mode3(all))
+      return e;
+    if (int e = v3_upload_constants_mode4(all))
+      return e;
     return SPIRK_OK;
   }
 
