@@ -138,7 +138,8 @@ def main():
         if rank != 0:
             return 0
         ref = cpu_reference_run(a, q, "irk" if scheme == "spirk" else scheme, max(1, min(a.steps, 3)), 1)
-        sample = f"same scheme/q/degree at refinement r={ref['refine']} ({ref['n_dofs']} DoFs), {ref['cores']} OpenMP threads"
+        sample = (f"same scheme/q/degree at refinement r={ref['refine']} ({ref['n_dofs']} DoFs), {ref['cores']} OpenMP threads; "
+                  "restated reference algorithm (oracle/cpu_abi.cc under the same C++ host layer), not deal.II")
         line = {"impl": "reference", "metric": metric, "value": ref["value"], "unit": unit, "n_gpus": n_gpus, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ref["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
@@ -279,11 +280,13 @@ def main():
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
-        ref = cpu_reference_run(a, q, scheme, 2, 1)
-        cpu = {"value": ref["value"], "unit": unit, "cores": ref["cores"], "kind": "port",
-               "sample": f"same scheme/q/degree at r={ref['refine']} ({ref['n_dofs']} DoFs), 2 timed steps, "
-                         f"{ref['cores']} OpenMP threads; restated reference algorithm, not deal.II",
-               "ms_per_step": ref["ms_per_step"]}
+        # in a process of its own: the CUDA libraries of this process are loaded RTLD_GLOBAL, a CPU double loaded
+        # beside them would bind to their symbols and silently run on the GPU
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                              "--cpu-refine", str(a.cpu_refine), "--degree", str(a.degree), "--stages", str(q), "--scheme", scheme,
+                              "--outer-tolerance", str(a.outer_tolerance)], capture_output=True, text=True, check=True)
+        ref = json.loads(out.stdout.strip().splitlines()[-1])
+        cpu = dict(ref["cpu_baseline"], ms_per_step=ref["ms_per_step"])
 
     if rank == 0:
         value = n_dofs * q / t_step * 1e-9
