@@ -386,16 +386,11 @@ namespace spirk
                 }
               else
                 {
-                  double am[K], ak[K], cmix[K];
-#pragma unroll
-                  for (int i = 0; i < K; ++i)
-                    cmix[i] = 0.0, am[i] = 0.0, ak[i] = 0.0;
-#pragma unroll
-                  for (int jb = 0; jb < NBC; ++jb)
+                  if constexpr (NBC == 1)
                     {
-                      // coupled: block jb's staged plane (its row parity differs by the parity of the block distance)
-                      const int     pj = (NBC == 1) ? xpar : (xpar ^ (((jb - b) & 1) & (int)(a.rows_per_block & 1)));
-                      const double *ur = xub + jb * (2 * UB) + urow(row, pj) + K * seg;
+                      // one block: row by row, every output stored as soon as it is complete (few live registers: the
+                      // z-sums of this thread stay in registers across the x-phase)
+                      const double *ur = xub + urow(row, xpar) + K * seg;
                       double        u[2 * K + 1];
 #pragma unroll
                       for (int j = 0; j < 2 * K + 1; ++j)
@@ -416,74 +411,133 @@ namespace spirk
                       if (CF)
                         {
                           // first Chebyshev iterate x1 = f0 D^-1 b formed on the fly (node class = position in the cell)
-                          const double *d1 = SD1 + ((((xP % K) + K) % K) * K + (row % K)) * K;
+                          const double *d1 = SD1 + ((xP % K) * K + (row % K)) * K;
 #pragma unroll
                           for (int j = 0; j < 2 * K + 1; ++j)
                             u[j] *= d1[j % K];
                         }
-                      // mass sweep of this block; vertex row: two partial sums (short dependency chains)
-                      double mj[K];
                       {
-                        double m1 = MC(0, 1) * u[K + 1];
-                        mj[0]     = Mv * u[K];
+                        // vertex row: two partial sums each (short dependency chains)
+                        double a0 = Mv * u[K], k0 = Kv * u[K], m1 = MC(0, 1) * u[K + 1], k1 = KC(0, 1) * u[K + 1];
 #pragma unroll
                         for (int j = 0; j < K; ++j)
-                          mj[0] = fma(MC(K, j), u[j], mj[0]);
+                          a0 = fma(MC(K, j), u[j], a0), k0 = fma(KC(K, j), u[j], k0);
 #pragma unroll
                         for (int j = 2; j <= K; ++j)
-                          m1 = fma(MC(0, j), u[K + j], m1);
-                        mj[0] += m1;
+                          m1 = fma(MC(0, j), u[K + j], m1), k1 = fma(KC(0, j), u[K + j], k1);
+                        oa[0] = a0 + m1, oc[0] = k0 + k1;
                       }
 #pragma unroll
                       for (int i = 1; i < K; ++i)
                         {
-                          mj[i] = MC(i, 0) * u[K];
+                          double ai = MC(i, 0) * u[K], ki = KC(i, 0) * u[K];
 #pragma unroll
                           for (int j = 1; j <= K; ++j)
-                            mj[i] = fma(MC(i, j), u[K + j], mj[i]);
+                            ai = fma(MC(i, j), u[K + j], ai), ki = fma(KC(i, j), u[K + j], ki);
+                          oa[i] = ai, oc[i] = ki;
                         }
-                      if (NBC > 1)
-                        {
-                          const double cbj = a.cc[b * NBC + jb];
+                    }
+                  else
+                    {
+                    double am[K], ak[K], cmix[K];
 #pragma unroll
-                          for (int i = 0; i < K; ++i)
-                            cmix[i] = fma(cbj, mj[i], cmix[i]);
-                        }
-                      if (NBC == 1 || jb == b)
-                        {
-                          // stiffness sweep (K' for plain operators) of the block this CTA produces
+                    for (int i = 0; i < K; ++i)
+                      cmix[i] = 0.0, am[i] = 0.0, ak[i] = 0.0;
 #pragma unroll
-                          for (int i = 0; i < K; ++i)
-                            am[i] = mj[i];
-                          double k1 = KC(0, 1) * u[K + 1];
-                          ak[0]     = Kv * u[K];
+                    for (int jb = 0; jb < NBC; ++jb)
+                      {
+                        // coupled: block jb's staged plane (its row parity differs by the parity of the block distance)
+                        const int     pj = (NBC == 1) ? xpar : (xpar ^ (((jb - b) & 1) & (int)(a.rows_per_block & 1)));
+                        const double *ur = xub + jb * (2 * UB) + urow(row, pj) + K * seg;
+                        double        u[2 * K + 1];
+#pragma unroll
+                        for (int j = 0; j < 2 * K + 1; ++j)
+                          u[j] = ur[j];
+                        if (edge_x)
+                          {
+                            if (seg == 0 && tx == 0)
+                              { // x < 0 (outside) and x = 0 (Dirichlet)
+#pragma unroll
+                                for (int j = 0; j <= K; ++j)
+                                  u[j] = 0.0;
+                              }
+                            if (seg == 1 && tx == 0)
+                              u[0] = 0.0; // x = 0 seen from the second cell
+                            if (seg == TX - 1 && tx == a.ntx - 1)
+                              u[2 * K] = 0.0; // x = n1-1 (Dirichlet)
+                          }
+                        if (CF)
+                          {
+                            // first Chebyshev iterate x1 = f0 D^-1 b formed on the fly (node class = position in the cell)
+                            const double *d1 = SD1 + ((((xP % K) + K) % K) * K + (row % K)) * K;
+#pragma unroll
+                            for (int j = 0; j < 2 * K + 1; ++j)
+                              u[j] *= d1[j % K];
+                          }
+                        // mass sweep of this block; vertex row: two partial sums (short dependency chains)
+                        double mj[K];
+                        {
+                          double m1 = MC(0, 1) * u[K + 1];
+                          mj[0]     = Mv * u[K];
 #pragma unroll
                           for (int j = 0; j < K; ++j)
-                            ak[0] = fma(KC(K, j), u[j], ak[0]);
+                            mj[0] = fma(MC(K, j), u[j], mj[0]);
 #pragma unroll
                           for (int j = 2; j <= K; ++j)
-                            k1 = fma(KC(0, j), u[K + j], k1);
-                          ak[0] += k1;
-#pragma unroll
-                          for (int i = 1; i < K; ++i)
-                            {
-                              ak[i] = KC(i, 0) * u[K];
-#pragma unroll
-                              for (int j = 1; j <= K; ++j)
-                                ak[i] = fma(KC(i, j), u[K + j], ak[i]);
-                            }
+                            m1 = fma(MC(0, j), u[K + j], m1);
+                          mj[0] += m1;
                         }
-                    }
-                  if (NBC > 1)
-                    {
-                      // dst_b = cl_b K u_b + M sum_j C_bj u_j: a = cl Mx u_b, c = cl Kx u_b + sum_j C_bj Mx u_j
 #pragma unroll
-                      for (int i = 0; i < K; ++i)
-                        ak[i] = fma(cl, ak[i], cmix[i]), am[i] *= cl;
-                    }
+                        for (int i = 1; i < K; ++i)
+                          {
+                            mj[i] = MC(i, 0) * u[K];
 #pragma unroll
-                  for (int i = 0; i < K; ++i)
-                    oa[i] = am[i], oc[i] = ak[i];
+                            for (int j = 1; j <= K; ++j)
+                              mj[i] = fma(MC(i, j), u[K + j], mj[i]);
+                          }
+                        if (NBC > 1)
+                          {
+                            const double cbj = a.cc[b * NBC + jb];
+#pragma unroll
+                            for (int i = 0; i < K; ++i)
+                              cmix[i] = fma(cbj, mj[i], cmix[i]);
+                          }
+                        if (NBC == 1 || jb == b)
+                          {
+                            // stiffness sweep (K' for plain operators) of the block this CTA produces
+#pragma unroll
+                            for (int i = 0; i < K; ++i)
+                              am[i] = mj[i];
+                            double k1 = KC(0, 1) * u[K + 1];
+                            ak[0]     = Kv * u[K];
+#pragma unroll
+                            for (int j = 0; j < K; ++j)
+                              ak[0] = fma(KC(K, j), u[j], ak[0]);
+#pragma unroll
+                            for (int j = 2; j <= K; ++j)
+                              k1 = fma(KC(0, j), u[K + j], k1);
+                            ak[0] += k1;
+#pragma unroll
+                            for (int i = 1; i < K; ++i)
+                              {
+                                ak[i] = KC(i, 0) * u[K];
+#pragma unroll
+                                for (int j = 1; j <= K; ++j)
+                                  ak[i] = fma(KC(i, j), u[K + j], ak[i]);
+                              }
+                          }
+                      }
+                    if (NBC > 1)
+                      {
+                        // dst_b = cl_b K u_b + M sum_j C_bj u_j: a = cl Mx u_b, c = cl Kx u_b + sum_j C_bj Mx u_j
+#pragma unroll
+                        for (int i = 0; i < K; ++i)
+                          ak[i] = fma(cl, ak[i], cmix[i]), am[i] *= cl;
+                      }
+#pragma unroll
+                    for (int i = 0; i < K; ++i)
+                      oa[i] = am[i], oc[i] = ak[i];
+                    }
                 }
             }
         };
