@@ -36,6 +36,7 @@ def main(argv=None):
     if world > 1:
         import torch
         import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         buf = C.create_string_buffer(128)
         if rank == 0:
