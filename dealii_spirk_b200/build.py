@@ -47,9 +47,12 @@ def build_device(force=False, verbose_ptxas=False):
     if verbose_ptxas:
         base.insert(1, "-Xptxas=-v")
     procs, objs = [], []
+    headers = [s_ for s_ in srcs if not s_.endswith(".cu")]
     for u in units:
         obj = os.path.join(objdir, u[:-3] + ".o")
         objs.append(obj)
+        if not force and not _newer(obj, headers + [os.path.join(csrc, u)]):
+            continue  # this unit is up to date (a unit depends on its own source and the headers)
         cmd = base + ["-c", "-o", obj, os.path.join(csrc, u)]
         print("+", " ".join(cmd), flush=True)
         procs.append((u, subprocess.Popen(cmd)))

@@ -337,6 +337,7 @@ struct spirk_graph
 {
   cudaGraph_t     graph = nullptr;
   cudaGraphExec_t exec  = nullptr;
+  size_t          n_kernels = 0; // kernel nodes of the captured sequence (for the launch count)
 };
 int spirk_graph_begin(spirk_ctx *ctx)
 {
@@ -357,13 +358,27 @@ int spirk_graph_end(spirk_ctx *ctx, spirk_graph **out)
       cudaGetLastError();
       return set_error(SPIRK_ERR_DEVICE, std::string("graph capture: ") + cudaGetErrorString(e));
     }
+  {
+    size_t n = 0;
+    if (cudaGraphGetNodes(g->graph, nullptr, &n) == cudaSuccess && n > 0)
+      {
+        std::vector<cudaGraphNode_t> nodes(n);
+        if (cudaGraphGetNodes(g->graph, nodes.data(), &n) == cudaSuccess)
+          for (size_t i = 0; i < n; ++i)
+            {
+              cudaGraphNodeType t;
+              if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
+                g->n_kernels++;
+            }
+      }
+  }
   *out = g;
   return SPIRK_OK;
 }
 int spirk_graph_launch(spirk_ctx *ctx, spirk_graph *g)
 {
   SPIRK_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
-  ctx->launches++;
+  ctx->launches += (long long)std::max<size_t>(1, g->n_kernels); // every replayed kernel counts
   return SPIRK_OK;
 }
 int spirk_graph_destroy(spirk_graph *g)
