@@ -45,7 +45,10 @@ def parse():
     ap.add_argument("--stages", type=int, default=0, help="RK stages q (default: 2 at N=1, N otherwise)")
     ap.add_argument("--scheme", default="", help="irk | spirk | irk_batched | complex_* (default irk at N=1, spirk else)")
     ap.add_argument("--outer-tolerance", type=float, default=1e-8, help="reference default main.cc:2964")
-    ap.add_argument("--cpu-refine", type=int, default=4, help="refinement of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-refine-min", type=int, default=4, help="smallest refinement of the bounded CPU sample")
+    ap.add_argument("--cpu-refine-max", type=int, default=6, help="largest refinement of the bounded CPU sample")
+    ap.add_argument("--cpu-budget", type=float, default=0.0,
+                    help="seconds of CPU work for the CPU leg (default: 200 for --impl reference, 25 for the cpu_baseline of the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true",
                     help="bracket the timed device-resident steps with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -96,26 +99,75 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def cpu_reference_run(a, q, scheme, n_steps, warmup):
-    """the restated reference algorithm on the host cores (bounded sample: refinement a.cpu_refine)"""
-    from dealii_spirk_b200 import hostapi
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
-    host = hostapi.HostLib(os.path.join(ROOT, "oracle", "_build", "libspirk_host_cpu.so"), TABLES)
+def _native_cpu_libs():
+    """The CPU restatement compiled -O3 -march=native ON THIS HOST (directory keyed by the host CPU, so a build made
+    on another machine is never executed here); falls back to the portable x86-64-v3 build."""
+    import hashlib
+    try:
+        info = open("/proc/cpuinfo").read()
+        key = [l for l in info.splitlines() if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        key = []
+    tag = hashlib.sha1("\n".join(key).encode()).hexdigest()[:10]
+    out = "_build_native_" + tag
+    try:
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "native", "NATIVE_OUT=" + out],
+                              stdout=subprocess.DEVNULL)
+        return os.path.join(ROOT, "oracle", out), "-O3 -march=native"
+    except (subprocess.CalledProcessError, OSError):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "all"])
+        return os.path.join(ROOT, "oracle", "_build"), "-O3 -march=x86-64-v3"
+
+
+def cpu_reference_run(a, q, scheme, n_steps, warmup, budget_s):
+    """The restated reference algorithm (oracle/cpu_abi.cc under the same C++ host layer) on the host cores.
+    A step is a BOUNDED SAMPLE of the GPU arm's workload: same scheme / q / degree / dt / tolerances at the largest
+    refinement r <= a.refine for which warmup + n_steps steps fit into budget_s (a step costs ~8.5x more per
+    refinement).  Everything returned describes what was actually run."""
+    from dealii_spirk_b200 import capi, hostapi
+    libdir, flags = _native_cpu_libs()
+    host = hostapi.HostLib(os.path.join(libdir, "libspirk_host_cpu.so"), TABLES)
     cores = os.cpu_count() or 1
-    r = a.cpu_refine
-    with hostapi.Run(host, params(scheme, a.degree, r, q, a.outer_tolerance, n_steps + warmup), dim=3) as run:
-        run.set_compute_errors(False)
-        run.setup()
-        n = run.scalar("n_dofs")
-        for _ in range(warmup):
-            run.step()
-        t0 = time.perf_counter()
-        for _ in range(n_steps):
-            run.step()
-        dt = (time.perf_counter() - t0) / n_steps
-        outer = run.array("outer_iterations")
-    return {"value": n * q / dt * 1e-9, "ms_per_step": dt * 1e3, "cores": cores, "n_dofs": int(n), "refine": r,
-            "outer_iterations": outer.tolist()}
+
+    def timed(r, steps, warm):
+        t_begin = time.perf_counter()
+        with hostapi.Run(host, params(scheme, a.degree, r, q, a.outer_tolerance, steps + warm), dim=3) as run:
+            run.set_compute_errors(False)
+            run.setup()
+            n = run.scalar("n_dofs")
+            for _ in range(warm):
+                run.step()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                run.step()
+            dt = (time.perf_counter() - t0) / steps
+            outer = run.array("outer_iterations")[-steps:]
+        return dt, int(n), outer.tolist(), time.perf_counter() - t_begin
+
+    r = min(a.cpu_refine_min, a.refine)
+    dt, n, outer, total = timed(r, 1, 1)  # calibration
+    spent = total
+    steps, warm = n_steps, warmup
+    while r < min(a.refine, a.cpu_refine_max) and spent + 8.5 * dt * (steps + warm + 1.5) <= budget_s:
+        r, dt = r + 1, 8.5 * dt
+    if spent + dt * (steps + warm + 1.5) > budget_s:  # even the smallest sample does not fit: fewer steps, said so
+        steps = max(1, min(steps, int((budget_s - spent) / dt) - 2))
+        warm = 1
+    dt, n, outer, total = timed(r, steps, warm)
+    # stage-vmult throughput of the CPU cell loop at the same refinement (the other half of the metric)
+    dev = capi.DeviceLib(os.path.join(libdir, "libspirk_cpu.so"))
+    lvl = capi.Level(3, a.degree, 2 ** r, 0)
+    with capi.Context(dev) as ctx:
+        src, dst = ctx.alloc(lvl.n_dofs), ctx.alloc(lvl.n_dofs)
+        ctx.call("spirk_vec_set", src, lvl.n_dofs, 0.5)
+        op = capi.real_op([16.0], [0.1])
+        ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, lvl.n_dofs)
+        t0, reps = time.perf_counter(), 3
+        for _ in range(reps):
+            ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, lvl.n_dofs)
+        vm = lvl.n_dofs * reps / (time.perf_counter() - t0) * 1e-9
+    return {"value": n * q / dt * 1e-9, "ms_per_step": dt * 1e3, "cores": cores, "n_dofs": n, "refine": r, "steps": steps,
+            "warmup": warm, "outer_iterations": outer, "vmult_gdofs": vm, "flags": flags, "scheme": scheme}
 
 
 def main():
@@ -137,15 +189,26 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return 0
-        ref = cpu_reference_run(a, q, "irk" if scheme == "spirk" else scheme, max(1, min(a.steps, 3)), 1)
-        sample = (f"same scheme/q/degree at refinement r={ref['refine']} ({ref['n_dofs']} DoFs), {ref['cores']} OpenMP threads; "
+        # one CPU process: the stage-parallel scheme is run as its single-process twin (same algebra, main.cc:815-974)
+        cpu_scheme = {"spirk": "irk", "complex_spirk": "complex_irk", "complex_spirk_batched": "complex_irk_batched"}.get(scheme, scheme)
+        ref = cpu_reference_run(a, q, cpu_scheme, max(1, a.steps), max(0, a.warmup), a.cpu_budget or 200.0)
+        sample = (f"{cpu_scheme} q={q} Q{a.degree} at refinement r={ref['refine']} ({ref['n_dofs']} DoFs) instead of r={a.refine}, "
+                  f"{ref['steps']} timed + {ref['warmup']} warm-up steps, {ref['cores']} OpenMP threads, {ref['flags']}; "
                   "restated reference algorithm (oracle/cpu_abi.cc under the same C++ host layer), not deal.II")
-        line = {"impl": "reference", "metric": metric, "value": ref["value"], "unit": unit, "n_gpus": n_gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": ref["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        # the line describes what RAN: config / steps / warmup are the sample's, the GPU arm's workload is named beside it
+        ref_config = dict(config, workload=f"3D heat equation Q{a.degree}, {cpu_scheme} q={q}, GMG(Chebyshev 5)+GMRES, hypercube "
+                          f"r={ref['refine']} (bounded CPU sample of: {config['workload']})",
+                          n_dofs=ref["n_dofs"], refine=ref["refine"], parallelism=f"1 CPU process, {ref['cores']} OpenMP threads",
+                          l2_policy="n/a (CPU)", sample_of=config["workload"])
+        line = {"impl": "reference", "metric": metric, "value": ref["value"], "unit": unit, "n_gpus": n_gpus, "steps": ref["steps"],
+                "warmup": ref["warmup"], "ms_per_step": ref["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": ref_config,
                 "cpu_baseline": {"value": ref["value"], "unit": unit, "cores": ref["cores"], "kind": "port", "sample": sample},
                 "e2e": {"value": ref["value"], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "restated reference algorithm (cell-loop sum factorisation, deal.II conventions), not deal.II itself"}
+                "vmult_gdofs": ref["vmult_gdofs"], "outer_iterations": [int(x) for x in ref["outer_iterations"]],
+                "comparable": ref["refine"] == a.refine and cpu_scheme == scheme,
+                "note": "restated reference algorithm (cell-loop sum factorisation, deal.II conventions), not deal.II itself; "
+                        "a bounded sample: throughput in DoF*stage/s is comparable across refinements, ms_per_step is not"}
         print(json.dumps(line))
         return 0
 
@@ -283,10 +346,13 @@ def main():
         # in a process of its own: the CUDA libraries of this process are loaded RTLD_GLOBAL, a CPU double loaded
         # beside them would bind to their symbols and silently run on the GPU
         out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
-                              "--cpu-refine", str(a.cpu_refine), "--degree", str(a.degree), "--stages", str(q), "--scheme", scheme,
-                              "--outer-tolerance", str(a.outer_tolerance)], capture_output=True, text=True, check=True)
+                              "--cpu-budget", str(a.cpu_budget or 25.0), "--cpu-refine-min", str(a.cpu_refine_min),
+                              "--cpu-refine-max", str(a.cpu_refine_max), "--refine", str(a.refine), "--degree", str(a.degree),
+                              "--stages", str(q), "--scheme", scheme, "--outer-tolerance", str(a.outer_tolerance)],
+                             capture_output=True, text=True, check=True)
         ref = json.loads(out.stdout.strip().splitlines()[-1])
-        cpu = dict(ref["cpu_baseline"], ms_per_step=ref["ms_per_step"])
+        cpu = dict(ref["cpu_baseline"], ms_per_step=ref["ms_per_step"], vmult_gdofs=ref["vmult_gdofs"], refine=ref["config"]["refine"],
+                   steps=ref["steps"])
 
     if rank == 0:
         value = n_dofs * q / t_step * 1e-9

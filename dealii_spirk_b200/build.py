@@ -31,19 +31,22 @@ def device_sources():
     return [os.path.join(d, f) for f in sorted(os.listdir(d))] + [os.path.join(ROOT, "include", "spirk_b200.h")]
 
 
-def build_device(force=False, verbose_ptxas=False):
+def build_device(force=False, verbose_ptxas=False, defines=(), out=None, objdir=None):
     """One object per translation unit (the main unit + one unit per mode of the plane-streaming cell operator,
     csrc/v3_mode*.cu), compiled side by side, each single-threaded: nvcc --split-compile gave a different register
     allocation of the hot kernels from build to build (see profiles/README.md), separate units are deterministic."""
     srcs = device_sources()
-    if not force and not _newer(DEVICE_LIB, srcs):
-        return DEVICE_LIB
+    out = out or DEVICE_LIB
+    if not force and not _newer(out, srcs):
+        return out
     csrc = os.path.join(HERE, "csrc")
     units = ["spirk_b200.cu"] + sorted(f for f in os.listdir(csrc) if f.startswith("v3_mode") and f.endswith(".cu"))
-    objdir = os.path.join(HERE, "build")
+    objdir = objdir or os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    # (the CUDA runtime is linked statically, nvcc's default: the library must not depend on which libcudart the
+    # Python environment happens to put first on the loader path)
     base = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ccbin", GXX,
-            "-Xcompiler", "-fPIC,-O3"]
+            "-Xcompiler", "-fPIC,-O3"] + ["-D" + d for d in defines]
     if verbose_ptxas:
         base.insert(1, "-Xptxas=-v")
     procs, objs = [], []
@@ -59,8 +62,17 @@ def build_device(force=False, verbose_ptxas=False):
     for u, p in procs:
         if p.wait() != 0:
             raise subprocess.CalledProcessError(p.returncode, u)
-    _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", GXX, "-o", DEVICE_LIB] + objs + ["-ldl"])
-    return DEVICE_LIB
+    _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-ccbin", GXX, "-o", out] + objs + ["-ldl"])
+    return out
+
+
+def build_variant(tag, defines, force=False):
+    """A kernel-experiment build of the device library with extra -D flags (SPIRK_V3_MINB / _NBUF / _NAC ...):
+    dealii_spirk_b200/variants/libspirk_b200_<tag>.so, loaded by tools/bench_vmult.py --lib."""
+    vdir = os.path.join(HERE, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    return build_device(force, defines=defines, out=os.path.join(vdir, f"libspirk_b200_{tag}.so"),
+                        objdir=os.path.join(vdir, "obj_" + tag))
 
 
 def host_sources():

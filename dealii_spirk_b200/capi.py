@@ -120,6 +120,9 @@ _SIGS = {
                        C.c_int, C.c_double],
     "spirk_mix_peer_a2a": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, dp,
                            C.c_int, C.c_double],
+    "spirk_mix_peer_a2a_contract": [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, dp, C.c_double],
+    "spirk_mix_peer_a2a_finish": [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int],
+    "spirk_xbuf_create_virtual_group": [C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_void_p)],
 }
 # every symbol include/spirk_b200.h declares (tests check the library exports all of them)
 ALL_SYMBOLS = sorted(list(_SIGS) + ["spirk_backend", "spirk_last_error", "spirk_ctx_launch_count",

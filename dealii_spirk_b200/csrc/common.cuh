@@ -93,15 +93,33 @@ struct spirk_ctx
   // small 1-D table scratch
   double *d_tab   = nullptr;
   size_t  tab_cap = 0;
+  // work queue of the plane-streaming cell operator (op_v3.cuh): [0] next item, [1] finished CTAs, [4...] boundary states;
+  // partial sums exchanged at the range boundaries
+  int    *d_v3_sched     = nullptr;
+  size_t  v3_sched_cap   = 0;
+  double *d_v3_carry     = nullptr;
+  size_t  v3_carry_cap   = 0;
+  std::vector<void *> retired; // outgrown queue arrays, kept alive for captured graphs
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   spirk_comm *reduction_comm = nullptr;
-  int         opt_apply_variant = 0;
+  // spirk_ctx_set_option knobs (documented in include/spirk_b200.h); defaults = the validated fastest configuration
+  int opt_apply_variant  = 0;  // "apply_variant": 0 plane streaming (op_v3), 2 / 3 tile columns (op_v2), 1 general cell kernel only
+  int opt_v3_schedule    = -1; // "v3_schedule": -1 / 2 work queue + carry exchange (default), 0 even static split, 1 z-lockstep,
+                               // 3 the round-1 heuristic (lockstep for vectors beyond the L2 capacity, else even split)
+  int opt_v3_chunk       = 0;  // "v3_chunk": layers per work item (0 = 8)
+  int opt_transfer_variant = 0; // "transfer_variant": 0 owner-computes 1-D sweeps, 1 cell-based kernels (restriction with atomics)
+  int opt_v3_grid        = 0;  // "v3_grid": 0 = all co-resident CTAs, > 0 = this many CTAs (even split)
+  int opt_v3_smem_pad_kb = 0;  // "v3_smem_pad_kb": extra dynamic shared memory per CTA (limits the CTAs per SM; experiments)
+  int opt_v3_npt         = 0;  // "v3_npt": nodes per y+z thread on 8 x 8 tiles, 0 = per mode (4 apply, 2 fused epilogues)
+  int opt_v3_small_below = 32; // "v3_small_below": levels with fewer cells per direction use 4 x 4-cell tiles
+  int opt_v3_l2promo     = 0;  // "v3_l2promo": CUtensorMapL2promotion of the staging maps (0 none .. 3 256 B)
 };
 
 namespace spirk
 {
   int ensure_scratch(spirk_ctx *ctx, size_t n);
   int ensure_tab(spirk_ctx *ctx, size_t n);
+  int ensure_v3_queue(spirk_ctx *ctx, size_t n_states, size_t n_carry);
   int upload_fe_constants();
   // host copy of the reference matrices as uploaded (exactly persymmetric), (k+1)^2 entries each
   void fe_host_sym(int k, double *Mh, double *Kh);

@@ -4,6 +4,9 @@
 
 namespace spirk
 {
+#define SPIRK_GRID_STRIDE(i, n) \
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
   // =========================================================================================
   // two-level transfer (deal.II MGTwoLevelTransfer set up in preconditioner.h:266-282)
   // One thread block per (coarse cell, vector block); sum-factorised with the (2k+1) x (k+1)
@@ -163,6 +166,105 @@ namespace spirk
       }
   }
 
+
+  // =========================================================================================
+  // two-level transfer, owner-computes form: three (two in 2-D) banded 1-D sweeps, one per direction
+  // (R = P^T = R1 (x) R1 (x) R1, P = P1 (x) P1 (x) P1 with the GLOBAL 1-D embedding P1: fine node j in coarse cell e
+  // takes the (2k+1) x (k+1) cell embedding, row j - 2k e).  One thread per OUTPUT entry: no zero-initialisation, no
+  // atomics, bitwise reproducible; every sweep is coalesced along x.  Restriction contracts x first (N_f -> N_f / 2 ->
+  // N_f / 4 -> N_f / 8), prolongation expands z first and adds into the fine vector in the last sweep.
+  // `d` = direction of the sweep; ex / ey / ez = extents of the OUTPUT array; the input differs in extent `d` only.
+  // =========================================================================================
+  struct Sweep1D
+  {
+    int       d, ex, ey, ez; // direction, output extents
+    int       n_in;          // input extent along d
+    int       ncc;           // coarse cells along d
+    long long N_out, N_in;   // entries per block
+  };
+  template <int K>
+  __global__ void __launch_bounds__(256) k_restrict_1d(const Sweep1D w, const int nb, double *__restrict__ out, const long long os,
+                                                       const double *__restrict__ in, const long long is)
+  {
+    constexpr int n = K + 1;
+    __shared__ double P[(2 * K + 1) * n]; // (the row index differs from lane to lane: shared memory, not the constant bank)
+    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
+      P[t] = c_fe[K].P[t];
+    __syncthreads();
+    SPIRK_GRID_STRIDE(e, w.N_out * nb)
+    {
+      const int       b  = (int)(e / w.N_out);
+      const long long r  = e - b * w.N_out;
+      const int       ox = (int)(r % w.ex), oy = (int)((r / w.ex) % w.ey), oz = (int)(r / ((long long)w.ex * w.ey));
+      const int       i  = (w.d == 0) ? ox : (w.d == 1 ? oy : oz); // coarse index along d
+      const int       n1c = K * w.ncc + 1;
+      double          s  = 0.0;
+      if (i > 0 && i < n1c - 1) // coarse Dirichlet entries stay 0
+        {
+          // input strides: the input has extent n_in along d, the output's extents elsewhere
+          const long long sx = 1, sy = (w.d == 0) ? w.n_in : w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
+          const long long sd = (w.d == 0) ? sx : (w.d == 1 ? sy : sz);
+          const long long base = b * is + ((w.d == 0) ? 0 : ox) + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz);
+          const int       ec = i / K, il = i - ec * K;
+          if (il != 0)
+            {
+              const double *p = in + base + (long long)(2 * K * ec) * sd;
+#pragma unroll
+              for (int jl = 0; jl <= 2 * K; ++jl)
+                s = fma(P[jl * n + il], p[jl * sd], s);
+            }
+          else
+            {
+              // vertex node of the coarse mesh: the fine nodes of both adjacent coarse cells (the shared one once)
+              const double *p = in + base + (long long)(2 * K * ec) * sd;
+              s               = p[0];
+#pragma unroll
+              for (int jl = 1; jl <= 2 * K; ++jl)
+                s = fma(P[jl * n + 0], p[jl * sd], s);
+#pragma unroll
+              for (int jl = 0; jl < 2 * K; ++jl)
+                s = fma(P[jl * n + K], p[(jl - 2 * K) * sd], s);
+            }
+        }
+      out[b * os + r] = s;
+    }
+  }
+  template <int K, bool ADD>
+  __global__ void __launch_bounds__(256) k_prolongate_1d(const Sweep1D w, const int nb, double *__restrict__ out, const long long os,
+                                                         const double *__restrict__ in, const long long is)
+  {
+    constexpr int n = K + 1;
+    __shared__ double P[(2 * K + 1) * n];
+    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
+      P[t] = c_fe[K].P[t];
+    __syncthreads();
+    SPIRK_GRID_STRIDE(e, w.N_out * nb)
+    {
+      const int       b  = (int)(e / w.N_out);
+      const long long r  = e - b * w.N_out;
+      const int       ox = (int)(r % w.ex), oy = (int)((r / w.ex) % w.ey), oz = (int)(r / ((long long)w.ex * w.ey));
+      const int       j  = (w.d == 0) ? ox : (w.d == 1 ? oy : oz); // fine index along d
+      const long long sx = 1, sy = (w.d == 0) ? w.n_in : w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
+      const long long sd = (w.d == 0) ? sx : (w.d == 1 ? sy : sz);
+      const long long base = b * is + ((w.d == 0) ? 0 : ox) + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz);
+      const int       ec = min(j / (2 * K), w.ncc - 1), jl = j - 2 * K * ec;
+      const int       n1c = K * w.ncc + 1;
+      const double   *p  = in + base + (long long)(K * ec) * sd;
+      double          s  = 0.0;
+#pragma unroll
+      for (int il = 0; il <= K; ++il)
+        {
+          const int i = K * ec + il;
+          if (i > 0 && i < n1c - 1) // coarse Dirichlet entries are read as 0
+            s = fma(P[jl * n + il], p[il * sd], s);
+        }
+      if (ADD)
+        out[b * os + r] += s;
+      else
+        out[b * os + r] = s;
+    }
+  }
+
   // y_b = A x_b, tiny dense (coarse-grid solve): one block per vector block
   __global__ void k_dense_matvec(const int n, double *__restrict__ y, const double *__restrict__ x, const long long stride,
                                  const double *__restrict__ A0, const long long matrix_stride)
@@ -185,8 +287,6 @@ namespace spirk
   // =========================================================================================
   // vector kernels
   // =========================================================================================
-#define SPIRK_GRID_STRIDE(i, n) \
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
 
   __global__ void k_set(double *x, const long long n, const double v) { SPIRK_GRID_STRIDE(i, n) x[i] = v; }
   __global__ void k_scale(double *x, const long long n, const double a) { SPIRK_GRID_STRIDE(i, n) x[i] *= a; }

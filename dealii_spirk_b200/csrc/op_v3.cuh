@@ -60,13 +60,14 @@ namespace spirk
     static constexpr int OB   = OW * (OY / 2);
     static constexpr int PA   = OX | 1;         // odd pitch: lanes along y hit distinct banks
     static constexpr int NOPS = v3_nops(MODE);  // operand planes that travel with the staged plane
-#ifdef SPIRK_V3_EXPERIMENT_MINB
-    static constexpr int NBUF = 3;
+    // build-time overrides for kernel experiments (tools/build_variant.py): -DSPIRK_V3_NBUF / _NAC / _MINB
+#ifdef SPIRK_V3_NBUF
+    static constexpr int NBUF = SPIRK_V3_NBUF;
 #else
     static constexpr int NBUF = (NOPS == 0 && NBC == 1) ? 4 : 3; // ring depth (three / two planes in flight; 2 CTAs per SM must fit)
 #endif
-#ifdef SPIRK_V3_EXPERIMENT_MINB
-    static constexpr int NAC = 1;
+#ifdef SPIRK_V3_NAC
+    static constexpr int NAC = SPIRK_V3_NAC;
 #else
     static constexpr int NAC  = (NOPS == 2) ? 1 : 2; // a'/c tile double-buffered where shared memory allows
 #endif
@@ -85,14 +86,14 @@ namespace spirk
     static constexpr int NT   = ((NXT > NY ? NXT : NY) + 31) / 32 * 32; // one x task per thread; the threads beyond NY are helpers:
                                                                          // TMA issue, Dirichlet faces
     static constexpr int NH   = NT - NY;
-#ifdef SPIRK_V3_EXPERIMENT_MINB
-    static constexpr int MINB = SPIRK_V3_EXPERIMENT_MINB;
+#ifdef SPIRK_V3_MINB
+    static constexpr int MINB = SPIRK_V3_MINB;
 #else
     static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 3 : 6);
 #endif
     static constexpr unsigned BYTES_U = NBC * 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
-    static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 3 * K * K * K + NBUF);
-    static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0 && (NBC == 1 || NOPS == 0), "tile shape");
+    static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 3 * K * K * K + NBUF + 2);
+    static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0 && NPT <= 4 && (NBC == 1 || NOPS == 0), "tile shape");
     static constexpr int ISSUER = (NH > 0) ? NY : 0; // the thread that issues the TMA copies
     static_assert(UB % 16 == 0 && OB % 16 == 0 && OY % 2 == 0 && BW <= 256 && BH <= 256, "128-byte aligned TMA boxes");
   };
@@ -144,6 +145,14 @@ namespace spirk
     int           ntx, nty;
     long long     W; // nb * columns * layers
     int           lock_nch, lock_len; // > 0: z-lockstep schedule (CTA = one column x one of lock_nch equal layer ranges)
+    // dyn != 0: work-item schedule.  Items = (block, layer range of lock_len layers, column), dealt round robin to the CTAs in
+    // that order (concurrent CTAs work on neighbouring columns at similar heights); a range that starts above layer 0 does
+    // NOT recompute the layer below: the two CTAs that meet at a range boundary exchange the partial z-sums of the shared
+    // vertex plane through `carry` (whoever is ready first publishes, the other one adds and stores; a + b is commutative,
+    // so the result is bitwise reproducible)
+    int           dyn, n_items;
+    int          *state;  // per range boundary: 0 idle, 1 claimed by the first arrival, 2 its partial sums are published
+    double       *carry;  // per range boundary: OX * OY partial sums
     long long     rows_per_block; // stride / n1: the blocks continue the row sequence of block 0
     int           sh_src, sh_o0, sh_o1; // element shift of the 16-byte aligned map base below the vector
     alignas(64) CUtensorMap tm_src, tm_o0, tm_o1; // staged nodes; operand 0 (rhs | x_old); operand 1 (rhs)
@@ -213,6 +222,7 @@ namespace spirk
     double   *sm3  = sm3_raw + (((128u - (smem_u32(sm3_raw) & 127u)) & 127u) >> 3); // TMA boxes: 128-byte aligned
     double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K, *SD1 = SDI + K * K * K;
     uint64_t *BAR  = reinterpret_cast<uint64_t *>(SD1 + K * K * K);
+    int      *QS   = reinterpret_cast<int *>(BAR + NBUF); // [2] role at a range boundary
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
     const double  Mv = c_fe[K].Mv;
 #define MC(i, j) Mh[v3_canon<K>(i, j)]
@@ -240,7 +250,7 @@ namespace spirk
     // the L2 capacity - one column x one layer range per CTA with neighbouring CTAs on neighbouring columns at
     // the same height, so that the halo rows / columns shared by adjacent tiles meet in L2
     long long w = a.W * blockIdx.x / gridDim.x, w_end = a.W * (blockIdx.x + 1) / gridDim.x;
-    if (a.lock_nch > 0)
+    if (a.lock_nch > 0 && !a.dyn)
       {
         const long long colb = blockIdx.x % ((long long)ncols), rest = blockIdx.x / ncols;
         const int       ch = (int)(rest % a.lock_nch), bb = (int)(rest / a.lock_nch);
@@ -249,14 +259,35 @@ namespace spirk
       }
     int             b_tab = -1;
     unsigned        it0   = 0; // ring position of the piece's first plane (runs on across pieces)
-    while (w < w_end)
+    int             q_item = (int)blockIdx.x;
+    for (;;)
       {
-        // ------------------------------------------------------------------ decode the piece
-        const int       L0  = (int)(w % nc);
-        const long long t_  = w / nc;
-        const int       col = (int)(t_ % ncols), b = (int)(t_ / ncols);
-        const int       L1  = (int)min((long long)nc, L0 + (w_end - w));
-        w += L1 - L0;
+        // ------------------------------------------------------------------ next piece: block b, column col, layers [L0, L1)
+        int L0, L1, col, b;
+        if (a.dyn)
+          {
+            // items are dealt round robin (item = blockIdx.x + n gridDim.x: block-uniform, so everything derived from it
+            // lives in uniform registers; an atomic draw from a queue would cost ~25 vector registers per thread)
+            __syncthreads(); // the previous piece is finished (ring, a'/c tile, tables, QS)
+            if (q_item >= a.n_items)
+              break;
+            const int item = q_item;
+            q_item += (int)gridDim.x;
+            col            = item % ncols;
+            const int rest = item / ncols, ch = rest % a.lock_nch;
+            b              = rest / a.lock_nch;
+            L0 = min(nc, ch * a.lock_len), L1 = min(nc, (ch + 1) * a.lock_len);
+          }
+        else
+          {
+            if (w >= w_end)
+              break;
+            L0                 = (int)(w % nc);
+            const long long t_ = w / nc;
+            col = (int)(t_ % ncols), b = (int)(t_ / ncols);
+            L1 = (int)min((long long)nc, L0 + (w_end - w));
+            w += L1 - L0;
+          }
         const int       tx = col % a.ntx, ty = col / a.ntx;
         const int       gx0 = tx * OX, gy0 = ty * OY;
         const double    cm = a.cm[b], cl = a.cl[b], f1 = a.f1[b], f2 = a.f2[b], sc = a.sc[b], sc_inv = 1.0 / sc;
@@ -266,12 +297,14 @@ namespace spirk
         const double    Kv = kp[V3_NKP - 1];
         const long long boff = (long long)b * a.stride;
         const double   *src  = a.src + boff;
-        const int       zf   = (L0 > 0) ? L0 - 1 : 0;      // first layer that is processed (recomputed if < L0)
+        const int       zf   = (L0 > 0 && !a.dyn) ? L0 - 1 : L0; // first layer that is processed (recomputed if < L0)
+        const bool      carry_in = a.dyn && L0 > 0, carry_out = a.dyn && L1 < nc; // range boundaries shared with another CTA
         const int       nsteps = 1 + K * (L1 - zf);        // node planes K zf .. K L1
         const bool      has_xo = (a.x_old != nullptr);
         const bool      edge_x = (tx == 0) || (tx == a.ntx - 1);
 
-        __syncthreads(); // the previous piece is finished with the ring, the a'/c tile and the tables
+        if (!a.dyn)
+          __syncthreads(); // the previous piece is finished with the ring, the a'/c tile and the tables
         if ((MODE == V2_CHEB_OWN || MODE == V2_CHEB_FIRST) && b != b_tab)
           {
             // scaling by node class (position of the node inside its cell): -f2 / diag and its inverse
@@ -651,7 +684,7 @@ namespace spirk
               // -------------------------------------------------------------- linear part of the epilogue of this plane
               // the z-sums run on (A x) / sc - g with  g = rhs / sc (residual) | (rhs + ((1 + f1) x - f1 x_old) / (f2 dinv)) / sc
               // (Chebyshev); sc = the scalar factored out of the operator (see v3_apply)
-              const bool owned = (NOPS > 0 || CF) && (ZL > 0) && !zpl && (P >= K * L0) && (P < K * L1);
+              const bool owned = (NOPS > 0 || CF) && (ZL > 0 || carry_in) && !zpl && (P >= K * L0) && (P < K * L1);
               double     g[NPT];
 #pragma unroll
               for (int i = 0; i < NPT; ++i)
@@ -700,7 +733,7 @@ namespace spirk
 #pragma unroll
                     for (int i = 0; i < NPT; ++i)
                       acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
-                  if ((NOPS > 0 || CF) && ZL > 0)
+                  if ((NOPS > 0 || CF) && (ZL > 0 || carry_in))
                     {
 #pragma unroll
                       for (int i = 0; i < NPT; ++i)
@@ -719,51 +752,99 @@ namespace spirk
                       const int       gx = gx0 + xl, gy = gy0 + K * ys + i0; // first of the NPT nodes
                       const long long j0 = boff + gx + (long long)n1 * gy + plane * (K * Lc);
                       const bool      anyb = (gx == 0) || (gy == 0) || (Lc == 0);
-                      if (MODE == V2_CHEB)
+                      const double   *sds  = SDS + i0 * K + (xl % K);
+                      const double    sca  = (MODE == V2_APPLY) ? sc : -sc;
+                      // final value of node i of plane z of the layer from its complete z-sum v
+                      auto store_node = [&](const int z, const int i, const double v) {
+                        const long long j = j0 + z * plane + i * n1;
+                        if (anyb && ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0)))
+                          v3_identity<MODE>(a, f1, f2, j, f0);
+                        else if (MODE == V2_CHEB)
+                          {
+                            // explicit inverse diagonal: operands straight from global memory
+                            const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
+                            a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - sc * v, fma(f1, x - xo, x));
+                          }
+                        else
+                          a.dst[j] = ((MODE == V2_CHEB_OWN || CF) ? sds[(z * K + i) * K] : sca) * v;
+                      };
+                      // The bottom plane of a range that starts above layer 0 (work-item schedule) also needs the z-sums of the
+                      // layer below, the top plane of a range that ends below the top those of the layer above: the two CTAs
+                      // meet at `state`; the first one publishes its partial sums, the second one adds them and stores.
+                      auto combine = [&](const int Lb, const double(&part)[NPT]) {
+                        const int bnd = (b * ncols + col) * a.lock_nch + Lb / a.lock_len;
+                        double   *cb  = a.carry + (size_t)bnd * (NY * NPT);
+                        if (tid == 0)
+                          QS[2] = atomicCAS(a.state + bnd, 0, 1);
+                        asm volatile("bar.sync 1, %0;" ::"r"(NY) : "memory");
+                        const int role = QS[2];
+                        if (role == 0)
+                          {
+#pragma unroll
+                            for (int i = 0; i < NPT; ++i)
+                              cb[i * NY + tid] = part[i];
+                            __threadfence();
+                            asm volatile("bar.sync 1, %0;" ::"r"(NY) : "memory");
+                            if (tid == 0)
+                              atomicExch(a.state + bnd, 2);
+                          }
+                        else
+                          {
+                            if (tid == 0)
+                              {
+                                while (atomicAdd(a.state + bnd, 0) != 2)
+                                  ;
+                                __threadfence();
+                              }
+                            asm volatile("bar.sync 1, %0;" ::"r"(NY) : "memory");
+                            // the plane is stored as plane 0 of layer Lb (this CTA sees it as z = K of layer Lb - 1 or as
+                            // z = 0 of layer Lb: same node class, same index)
+                            const long long jb = boff + gx + (long long)n1 * gy + plane * (K * Lb);
+#pragma unroll
+                            for (int i = 0; i < NPT; ++i)
+                              {
+                                const double    v = part[i] + __ldcg(cb + i * NY + tid);
+                                const long long j = jb + i * n1;
+                                if ((gx == 0) || (i == 0 && gy == 0))
+                                  v3_identity<MODE>(a, f1, f2, j, f0);
+                                else if (MODE == V2_CHEB)
+                                  {
+                                    const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
+                                    a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - sc * v, fma(f1, x - xo, x));
+                                  }
+                                else
+                                  a.dst[j] = ((MODE == V2_CHEB_OWN || CF) ? sds[i * K] : sca) * v;
+                              }
+                            asm volatile("bar.sync 1, %0;" ::"r"(NY) : "memory");
+                            if (tid == 0)
+                              a.state[bnd] = 0; // ready for the next launch
+                          }
+                      };
+                      const bool defer0 = carry_in && (Lc == L0);
+                      if (!anyb && !defer0 && MODE != V2_CHEB)
                         {
-                          // explicit inverse diagonal: operands straight from global memory
+                          double *dp = a.dst + j0;
 #pragma unroll
                           for (int z = 0; z < K; ++z)
 #pragma unroll
                             for (int i = 0; i < NPT; ++i)
-                              {
-                                const long long j = j0 + z * plane + i * n1;
-                                if (anyb && ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0)))
-                                  v3_identity<MODE>(a, f1, f2, j, f0);
-                                else
-                                  {
-                                    const double x = a.src[j], xo = has_xo ? a.x_old[j] : 0.0;
-                                    a.dst[j]       = fma(f2 * a.dinv[j], a.rhs[j] - sc * acc[z][i], fma(f1, x - xo, x));
-                                  }
-                              }
+                              dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN || CF) ? sds[(z * K + i) * K] : sca) * acc[z][i];
                         }
                       else
                         {
-                          double       *dp  = a.dst + j0;
-                          const double *sds = SDS + i0 * K + (xl % K);
-                          const double  sca = (MODE == V2_APPLY) ? sc : -sc;
-                          if (!anyb)
-                            {
 #pragma unroll
-                              for (int z = 0; z < K; ++z)
+                          for (int z = 0; z < K; ++z)
+                            if (!(z == 0 && defer0))
+                              {
 #pragma unroll
                                 for (int i = 0; i < NPT; ++i)
-                                  dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN || CF) ? sds[(z * K + i) * K] : sca) * acc[z][i];
-                            }
-                          else
-                            {
-#pragma unroll
-                              for (int z = 0; z < K; ++z)
-#pragma unroll
-                                for (int i = 0; i < NPT; ++i)
-                                  {
-                                    if ((gx == 0) || (i == 0 && gy == 0) || (z == 0 && Lc == 0))
-                                      v3_identity<MODE>(a, f1, f2, j0 + z * plane + i * n1, f0);
-                                    else
-                                      dp[z * plane + i * n1] = ((MODE == V2_CHEB_OWN || CF) ? sds[(z * K + i) * K] : sca) * acc[z][i];
-                                  }
-                            }
+                                  store_node(z, i, acc[z][i]);
+                              }
                         }
+                      if (defer0)
+                        combine(L0, acc[0]);
+                      if (carry_out && Lc == L1 - 1)
+                        combine(L1, acc[K]);
                     }
                   // the top plane becomes the bottom plane of the next layer
 #pragma unroll
@@ -855,31 +936,21 @@ namespace spirk
       }
     return fn;
   }
-  inline int v3_l2_promotion()
-  {
-    static int v = -1;
-    if (v < 0)
-      {
-        const char *e = getenv("SPIRK_V3_L2PROMO"); // tuning knob: 0 none, 1 64 B, 2 128 B, 3 256 B
-        v             = e ? atoi(e) : 0;
-      }
-    return v;
-  }
   inline int v3_make_map(CUtensorMap *map, int *shift, const double *ptr, const long long n_elems, const int n1, const int box_w,
-                         const int box_h)
+                         const int box_h, const int l2promo)
   {
     // the solver applies the operator to the same few vectors over and over: keep the encoded maps
     struct Entry
     {
       const double *ptr;
       long long     n_elems;
-      int           n1, box_w, box_h, shift;
+      int           n1, box_w, box_h, l2promo, shift;
       CUtensorMap   map;
     };
     static thread_local std::vector<Entry> cache;
     static thread_local size_t             next = 0;
     for (const Entry &e : cache)
-      if (e.ptr == ptr && e.n_elems == n_elems && e.n1 == n1 && e.box_w == box_w && e.box_h == box_h)
+      if (e.ptr == ptr && e.n_elems == n_elems && e.n1 == n1 && e.box_w == box_w && e.box_h == box_h && e.l2promo == l2promo)
         {
           *map = e.map, *shift = e.shift;
           return SPIRK_OK;
@@ -895,11 +966,11 @@ namespace spirk
     const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
     alignas(64) CUtensorMap tm;
     const CUresult   r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                             CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)v3_l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                             CU_TENSOR_MAP_SWIZZLE_NONE, (CUtensorMapL2promotion)l2promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
       return set_error(SPIRK_ERR_DEVICE, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     *map = tm;
-    Entry e{ptr, n_elems, n1, box_w, box_h, *shift, tm};
+    Entry e{ptr, n_elems, n1, box_w, box_h, l2promo, *shift, tm};
     if (cache.size() < 64)
       cache.push_back(e);
     else
@@ -911,45 +982,68 @@ namespace spirk
   int v3_launch_mode(spirk_ctx *ctx, V3Args &a)
   {
     using C = CfgV3<K, TX, TY, MODE, NPT, NBC>;
-    static bool attr_set = false;
-    if (!attr_set)
+    const size_t smem = C::smem + (size_t)std::max(0, ctx->opt_v3_smem_pad_kb) * 1024;
+    static size_t attr_set = 0;
+    if (attr_set != smem)
       {
-        SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE, NPT, NBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
-        attr_set = true;
+        SPIRK_CUDA(cudaFuncSetAttribute(k_v3<K, TX, TY, MODE, NPT, NBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = smem;
       }
+    const int       l2p     = ctx->opt_v3_l2promo;
     const long long n_elems = (long long)(a.nb - 1) * a.stride + a.g.N;
-    if (int e = v3_make_map(&a.tm_src, &a.sh_src, a.src, n_elems, a.g.n1, C::BW, C::BH))
+    if (int e = v3_make_map(&a.tm_src, &a.sh_src, a.src, n_elems, a.g.n1, C::BW, C::BH, l2p))
       return e;
     a.tm_o0 = a.tm_src, a.tm_o1 = a.tm_src, a.sh_o0 = a.sh_o1 = 0;
     const double *o0 = (MODE == V2_RESIDUAL) ? a.rhs : (MODE == V2_CHEB_OWN ? a.x_old : nullptr);
     if (o0 != nullptr)
-      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, o0, n_elems, a.g.n1, C::OW, C::OY / 2))
+      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, o0, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
         return e;
     if (MODE == V2_CHEB_OWN)
-      if (int e = v3_make_map(&a.tm_o1, &a.sh_o1, a.rhs, n_elems, a.g.n1, C::OW, C::OY / 2))
+      if (int e = v3_make_map(&a.tm_o1, &a.sh_o1, a.rhs, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
         return e;
-    // fixed grid: all co-resident CTAs, but no piece shorter than ~4 layers (a piece above layer 0
-    // recomputes one layer)
+    // Schedules (option "v3_schedule"): 2 (default) (block, layer range, column) items dealt round robin, with the partial sums
+    // of the shared vertex planes exchanged between neighbouring ranges (no recomputation, any number of items per CTA);
+    // 0 even static split of the (block, column, layer) space, 1 z-lockstep (one column x one of nch equal layer ranges per
+    // CTA) - in both a piece that starts above layer 0 recomputes the layer below it.
     const long long slots = (long long)ctx->n_sms * C::MINB;
-    long long       grid  = std::max(1LL, std::min(slots, a.W / 4));
-    a.lock_nch = 0, a.lock_len = 0;
-    {
-      static int force = -2;
-      if (force == -2)
-        {
-          const char *e = getenv("SPIRK_V3_LOCKSTEP"); // tuning knob: 0 off, 1 on, unset: by vector size
-          force         = e ? atoi(e) : -1;
-        }
-      const long long cols = (long long)a.nb * a.ntx * a.nty;
-      const int       nch  = (int)std::max(1LL, std::min(slots / cols, (long long)a.g.nc / 8)); // ranges of >= 8 layers
-      if (force == 1 || (force == -1 && 2 * cols * nch >= slots))
-        {
-          a.lock_len = (a.g.nc + nch - 1) / nch;
-          a.lock_nch = (a.g.nc + a.lock_len - 1) / a.lock_len;
-          grid       = cols * a.lock_nch;
-        }
-    }
-    k_v3<K, TX, TY, MODE, NPT, NBC><<<(unsigned int)grid, C::NT, C::smem, ctx->stream>>>(a);
+    long long       grid  = std::max(1LL, std::min(ctx->opt_v3_grid > 0 ? (long long)ctx->opt_v3_grid : slots, a.W / 4));
+    a.lock_nch = 0, a.lock_len = 0, a.dyn = 0, a.n_items = 0, a.state = nullptr, a.carry = nullptr;
+    const long long cols  = (long long)a.nb * a.ntx * a.nty;
+    const int       force = ctx->opt_v3_schedule;
+    if (force < 0 || force == 2)
+      {
+        // layers per item: as short as possible while the items do not outnumber the CTA slots, 8 at most (an item costs a
+        // pipeline fill and up to two boundary exchanges; measured r = 3 .. 7, profiles/README.md)
+        int len = 8;
+        if (ctx->opt_v3_chunk > 0)
+          len = ctx->opt_v3_chunk;
+        else
+          for (int c = 1; c < 8; c *= 2)
+            if (cols * ((a.g.nc + c - 1) / c) <= slots)
+              {
+                len = c;
+                break;
+              }
+        len = std::max(1, std::min(len, a.g.nc));
+        a.lock_len = len, a.lock_nch = (a.g.nc + len - 1) / len;
+        a.dyn      = 1;
+        a.n_items  = (int)(cols * a.lock_nch);
+        if (int e = ensure_v3_queue(ctx, (size_t)a.n_items, (size_t)a.n_items * C::NY * NPT))
+          return e;
+        a.state = ctx->d_v3_sched, a.carry = ctx->d_v3_carry;
+        grid    = std::max(1LL, std::min(ctx->opt_v3_grid > 0 ? (long long)ctx->opt_v3_grid : slots, (long long)a.n_items));
+      }
+    else if (ctx->opt_v3_grid <= 0)
+      {
+        const int nch = (int)std::max(1LL, std::min(slots / cols, (long long)a.g.nc / 8)); // ranges of >= 8 layers
+        if (force == 1 || (force == 3 && 2 * cols * nch >= slots))
+          {
+            a.lock_len = (a.g.nc + nch - 1) / nch;
+            a.lock_nch = (a.g.nc + a.lock_len - 1) / a.lock_len;
+            grid       = cols * a.lock_nch;
+          }
+      }
+    k_v3<K, TX, TY, MODE, NPT, NBC><<<(unsigned int)grid, C::NT, smem, ctx->stream>>>(a);
     SPIRK_LAUNCH_CHECK(ctx);
     return SPIRK_OK;
   }
@@ -1040,23 +1134,12 @@ namespace spirk
       }
     // 8 x 8-cell tiles (37/32 halo) on large levels; 4 x 4-cell tiles (21/16 halo, 4 x the columns) keep all SMs busy on
     // the coarser multigrid levels
-    static int small_below = -1;
-    if (small_below < 0)
-      {
-        const char *e = getenv("SPIRK_V3_SMALL_BELOW"); // tuning knob: levels with fewer cells per direction use 4 x 4 tiles
-        small_below   = e ? atoi(e) : 32; // measured (IRK q=2 step, r=6): 64 -> 48.2 ms, 32 -> 46.7 ms, 16 -> 47.0 ms
-      }
-    if (g.nc % 8 != 0 || g.nc < small_below)
+    // option "v3_small_below"; measured (IRK q=2 step, r=6): 64 -> 48.2 ms, 32 -> 46.7 ms, 16 -> 47.0 ms
+    if (g.nc % 8 != 0 || g.nc < ctx->opt_v3_small_below)
       return v3_launch<4, 4, 4, 4>(ctx, a, mode);
     // nodes per y+z thread on the 8 x 8 tile: 4 = 20 warps/SM at 96 registers, 2 = 32 warps/SM at 64 registers (some
     // spills); measured: 4 is better for the plain apply at r = 6, 2 for the fused epilogues
-    static int npt_env = -2;
-    if (npt_env == -2)
-      {
-        const char *e = getenv("SPIRK_V3_NPT"); // tuning knob
-        npt_env       = e ? atoi(e) : -1;
-      }
-    const int npt = (npt_env > 0) ? npt_env : (mode == V2_APPLY ? 4 : 2);
+    const int npt = (ctx->opt_v3_npt == 2 || ctx->opt_v3_npt == 4) ? ctx->opt_v3_npt : (mode == V2_APPLY ? 4 : 2);
     if (npt == 2)
       return v3_launch<4, 8, 8, 2>(ctx, a, mode);
     return v3_launch<4, 8, 8, 4>(ctx, a, mode);

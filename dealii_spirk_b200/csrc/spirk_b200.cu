@@ -95,10 +95,7 @@ namespace spirk
     if (ctx->scratch_cap < n)
       {
         if (ctx->d_scratch)
-          {
-            SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
-            SPIRK_CUDA(cudaFree(ctx->d_scratch));
-          }
+          ctx->retired.push_back(ctx->d_scratch); // a captured graph may still hold the old pointer
         ctx->d_scratch = nullptr, ctx->scratch_cap = 0;
         SPIRK_CUDA(cudaMalloc(&ctx->d_scratch, n * sizeof(double)));
         ctx->scratch_cap = n;
@@ -118,6 +115,32 @@ namespace spirk
         ctx->d_tab = nullptr, ctx->tab_cap = 0;
         SPIRK_CUDA(cudaMalloc(&ctx->d_tab, n * sizeof(double)));
         ctx->tab_cap = n;
+      }
+    return SPIRK_OK;
+  }
+
+  int ensure_v3_queue(spirk_ctx *ctx, size_t n_states, size_t n_carry)
+  {
+    // Grown arrays never replace the old ones in place: a captured CUDA graph may hold the old pointers, so those stay
+    // valid (and zeroed, as every launch leaves them) until the context is destroyed.
+    if (ctx->v3_sched_cap < n_states + 4)
+      {
+        if (ctx->d_v3_sched)
+          ctx->retired.push_back(ctx->d_v3_sched);
+        ctx->d_v3_sched = nullptr, ctx->v3_sched_cap = 0;
+        const size_t cap = 2 * (n_states + 4);
+        SPIRK_CUDA(cudaMalloc(&ctx->d_v3_sched, cap * sizeof(int)));
+        SPIRK_CUDA(cudaMemsetAsync(ctx->d_v3_sched, 0, cap * sizeof(int), ctx->stream)); // the kernels leave it zeroed
+        ctx->v3_sched_cap = cap;
+      }
+    if (ctx->v3_carry_cap < n_carry)
+      {
+        if (ctx->d_v3_carry)
+          ctx->retired.push_back(ctx->d_v3_carry);
+        ctx->d_v3_carry = nullptr, ctx->v3_carry_cap = 0;
+        const size_t cap = n_carry + n_carry / 2;
+        SPIRK_CUDA(cudaMalloc(&ctx->d_v3_carry, cap * sizeof(double)));
+        ctx->v3_carry_cap = cap;
       }
     return SPIRK_OK;
   }
@@ -295,6 +318,10 @@ int spirk_ctx_destroy(spirk_ctx *ctx)
   cudaFreeHost(ctx->h_result);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_tab);
+  cudaFree(ctx->d_v3_sched);
+  cudaFree(ctx->d_v3_carry);
+  for (void *p : ctx->retired)
+    cudaFree(p);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -324,11 +351,21 @@ int spirk_ctx_timer_end(spirk_ctx *ctx, double *ms)
 }
 int spirk_ctx_set_option(spirk_ctx *ctx, const char *name, int value)
 {
-  if (std::strcmp(name, "apply_variant") == 0)
-    {
-      ctx->opt_apply_variant = value;
-      return SPIRK_OK;
-    }
+  struct
+  {
+    const char *name;
+    int        *slot;
+  } const table[] = {{"apply_variant", &ctx->opt_apply_variant},   {"v3_schedule", &ctx->opt_v3_schedule},
+                     {"v3_grid", &ctx->opt_v3_grid},               {"v3_smem_pad_kb", &ctx->opt_v3_smem_pad_kb},
+                     {"v3_npt", &ctx->opt_v3_npt},                 {"v3_small_below", &ctx->opt_v3_small_below},
+                     {"v3_l2promo", &ctx->opt_v3_l2promo},         {"v3_chunk", &ctx->opt_v3_chunk},
+                     {"transfer_variant", &ctx->opt_transfer_variant}};
+  for (const auto &t : table)
+    if (std::strcmp(name, t.name) == 0)
+      {
+        *t.slot = value;
+        return SPIRK_OK;
+      }
   return set_error(SPIRK_ERR_INVALID, std::string("unknown option ") + name);
 }
 
@@ -612,6 +649,16 @@ int spirk_op_assemble_dense(spirk_ctx *ctx, const spirk_level *lvl, double mass,
 }
 
 // ------------------------------------------------------------------------------- transfer
+// the sweeps of the owner-computes transfer (misc_kernels.cuh): extents of the arrays between the sweeps
+static Sweep1D make_sweep(int d, int ex, int ey, int ez, int n_in, int ncc)
+{
+  Sweep1D w;
+  w.d = d, w.ex = ex, w.ey = ey, w.ez = ez, w.n_in = n_in, w.ncc = ncc;
+  w.N_out = (long long)ex * ey * ez;
+  w.N_in  = w.N_out / (d == 0 ? ex : (d == 1 ? ey : ez)) * n_in;
+  return w;
+}
+
 int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, double *fine, long long fs, const double *coarse,
                             long long cs)
 {
@@ -619,19 +666,48 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
     return e;
   if (lf->n_cells_1d % 2)
     return set_error(SPIRK_ERR_INVALID, "prolongate: fine level needs an even number of cells");
-  const Geo       g      = make_geo(lf);
-  const long long ncc    = g.nc / 2;
-  const long long ncells = (g.dim == 3 ? ncc * ncc * ncc : ncc * ncc) * nb;
-  const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 16);
+  const Geo g   = make_geo(lf);
+  const int ncc = g.nc / 2, nf = g.n1, ncn = g.k * ncc + 1;
+  if (ctx->opt_transfer_variant == 1)
+    {
+      const long long ncells = (g.dim == 3 ? (long long)ncc * ncc * ncc : (long long)ncc * ncc) * nb;
+      const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 16);
+      if (g.dim == 3)
+        {
+          SPIRK_DISPATCH_K(g.k, (k_prolongate_add<K, 3><<<grid, 128, 0, ctx->stream>>>(g, nb, fine, fs, coarse, cs)));
+        }
+      else
+        {
+          SPIRK_DISPATCH_K(g.k, (k_prolongate_add<K, 2><<<grid, 128, 0, ctx->stream>>>(g, nb, fine, fs, coarse, cs)));
+        }
+      SPIRK_LAUNCH_CHECK(ctx);
+      return SPIRK_OK;
+    }
+  // expand z, then y, then x (adding into the fine vector)
   if (g.dim == 3)
     {
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_add<K, 3><<<grid, 128, 0, ctx->stream>>>(g, nb, fine, fs, coarse, cs)));
+      const Sweep1D   wz = make_sweep(2, ncn, ncn, nf, ncn, ncc), wy = make_sweep(1, ncn, nf, nf, ncn, ncc), wx = make_sweep(0, nf, nf, nf, ncn, ncc);
+      if (int e = ensure_scratch(ctx, (size_t)nb * (wz.N_out + wy.N_out)))
+        return e;
+      double *t2 = ctx->d_scratch, *t1 = ctx->d_scratch + (size_t)nb * wz.N_out;
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, false><<<grid_for(ctx, wz.N_out * nb, 256), 256, 0, ctx->stream>>>(wz, nb, t2, wz.N_out, coarse, cs)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, false><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, t1, wy.N_out, t2, wz.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, true><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, fine, fs, t1, wy.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
     }
   else
     {
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_add<K, 2><<<grid, 128, 0, ctx->stream>>>(g, nb, fine, fs, coarse, cs)));
+      const Sweep1D wy = make_sweep(1, ncn, nf, 1, ncn, ncc), wx = make_sweep(0, nf, nf, 1, ncn, ncc);
+      if (int e = ensure_scratch(ctx, (size_t)nb * wy.N_out))
+        return e;
+      double *t1 = ctx->d_scratch;
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, false><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, t1, wy.N_out, coarse, cs)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, true><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, fine, fs, t1, wy.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
     }
-  SPIRK_LAUNCH_CHECK(ctx);
   return SPIRK_OK;
 }
 
@@ -642,24 +718,54 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
     return e;
   if (lf->n_cells_1d % 2)
     return set_error(SPIRK_ERR_INVALID, "restrict: fine level needs an even number of cells");
-  const Geo   g  = make_geo(lf);
-  spirk_level lc = *lf;
-  lc.n_cells_1d /= 2;
-  const Geo gc = make_geo(&lc);
-  for (int b = 0; b < nb; ++b)
-    SPIRK_CUDA(cudaMemsetAsync(coarse + b * cs, 0, gc.N * sizeof(double), ctx->stream));
-  const long long ncc    = g.nc / 2;
-  const long long ncells = (g.dim == 3 ? ncc * ncc * ncc : ncc * ncc) * nb;
-  const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 16);
+  const Geo g   = make_geo(lf);
+  const int ncc = g.nc / 2, nf = g.n1, ncn = g.k * ncc + 1;
+  if (ctx->opt_transfer_variant == 1)
+    {
+      // cell-based variant (atomics into a zeroed coarse vector; kept for A/B measurements)
+      spirk_level lc = *lf;
+      lc.n_cells_1d /= 2;
+      const Geo gc = make_geo(&lc);
+      for (int b = 0; b < nb; ++b)
+        SPIRK_CUDA(cudaMemsetAsync(coarse + b * cs, 0, gc.N * sizeof(double), ctx->stream));
+      const long long ncells = (g.dim == 3 ? (long long)ncc * ncc * ncc : (long long)ncc * ncc) * nb;
+      const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 16);
+      if (g.dim == 3)
+        {
+          SPIRK_DISPATCH_K(g.k, (k_restrict<K, 3><<<grid, 128, 0, ctx->stream>>>(g, nb, coarse, cs, fine, fs)));
+        }
+      else
+        {
+          SPIRK_DISPATCH_K(g.k, (k_restrict<K, 2><<<grid, 128, 0, ctx->stream>>>(g, nb, coarse, cs, fine, fs)));
+        }
+      SPIRK_LAUNCH_CHECK(ctx);
+      return SPIRK_OK;
+    }
+  // contract x, then y, then z: every coarse entry is written exactly once
   if (g.dim == 3)
     {
-      SPIRK_DISPATCH_K(g.k, (k_restrict<K, 3><<<grid, 128, 0, ctx->stream>>>(g, nb, coarse, cs, fine, fs)));
+      const Sweep1D wx = make_sweep(0, ncn, nf, nf, nf, ncc), wy = make_sweep(1, ncn, ncn, nf, nf, ncc), wz = make_sweep(2, ncn, ncn, ncn, nf, ncc);
+      if (int e = ensure_scratch(ctx, (size_t)nb * (wx.N_out + wy.N_out)))
+        return e;
+      double *t1 = ctx->d_scratch, *t2 = ctx->d_scratch + (size_t)nb * wx.N_out;
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, t1, wx.N_out, fine, fs)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, t2, wy.N_out, t1, wx.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wz.N_out * nb, 256), 256, 0, ctx->stream>>>(wz, nb, coarse, cs, t2, wy.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
     }
   else
     {
-      SPIRK_DISPATCH_K(g.k, (k_restrict<K, 2><<<grid, 128, 0, ctx->stream>>>(g, nb, coarse, cs, fine, fs)));
+      const Sweep1D wx = make_sweep(0, ncn, nf, 1, nf, ncc), wy = make_sweep(1, ncn, ncn, 1, nf, ncc);
+      if (int e = ensure_scratch(ctx, (size_t)nb * wx.N_out))
+        return e;
+      double *t1 = ctx->d_scratch;
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, t1, wx.N_out, fine, fs)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, coarse, cs, t1, wx.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
     }
-  SPIRK_LAUNCH_CHECK(ctx);
   return SPIRK_OK;
 }
 
@@ -957,6 +1063,7 @@ struct spirk_xbuf
   long long             n = 0;
   int                   rank = 0, n_ranks = 1;
   double               *d_sync = nullptr; // 1 double for the stream-ordered rank barrier
+  bool                  is_virtual = false; // member of a same-device group (spirk_xbuf_create_virtual_group)
 };
 
 int spirk_comm_xbuf_create(spirk_ctx *ctx, spirk_comm *c, long long n, spirk_xbuf **out)
@@ -967,33 +1074,71 @@ int spirk_comm_xbuf_create(spirk_ctx *ctx, spirk_comm *c, long long n, spirk_xbu
   spirk_xbuf *x = new spirk_xbuf();
   x->n = n, x->rank = c->rank, x->n_ranks = c->n_ranks;
   x->peer.assign(c->n_ranks, nullptr);
+  // A failure on ONE rank must not leave the others waiting in the collective below: every rank always takes part in
+  // the all-gather and ships a status byte next to its IPC handle; all ranks then agree on success or failure.
+  struct Packet
+  {
+    cudaIpcMemHandle_t handle;
+    int                ok;
+  };
+  Packet      mine;
+  std::string why;
+  std::memset(&mine, 0, sizeof(mine));
   // [0, n): this rank's published blocks; [n, 2n): result region the other ranks write into (spirk_mix_peer_a2a)
-  SPIRK_CUDA(cudaMalloc(&x->local, (size_t)2 * n * sizeof(double)));
-  SPIRK_CUDA(cudaMemsetAsync(x->local, 0, (size_t)2 * n * sizeof(double), ctx->stream));
-  SPIRK_CUDA(cudaMalloc(&x->d_sync, sizeof(double)));
-  SPIRK_CUDA(cudaMemsetAsync(x->d_sync, 0, sizeof(double), ctx->stream));
-  x->peer[c->rank] = x->local;
+  bool ok = cudaMalloc(&x->local, (size_t)2 * n * sizeof(double)) == cudaSuccess;
+  if (!ok)
+    why = "cudaMalloc of the exchange buffer failed", x->local = nullptr;
+  ok = ok && cudaMemsetAsync(x->local, 0, (size_t)2 * n * sizeof(double), ctx->stream) == cudaSuccess;
+  ok = ok && cudaMalloc(&x->d_sync, sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(x->d_sync, 0, sizeof(double), ctx->stream) == cudaSuccess;
+  if (ok && c->n_ranks > 1 && cudaIpcGetMemHandle(&mine.handle, x->local) != cudaSuccess)
+    ok = false, why = "cudaIpcGetMemHandle failed";
+  cudaGetLastError();
+  mine.ok = ok ? 1 : 0;
+  if (ok)
+    x->peer[c->rank] = x->local;
+  auto fail = [&](int code, const std::string &msg) {
+    for (int r = 0; r < c->n_ranks; ++r)
+      if (r != c->rank && x->peer[r])
+        cudaIpcCloseMemHandle(x->peer[r]);
+    if (x->local)
+      cudaFree(x->local);
+    if (x->d_sync)
+      cudaFree(x->d_sync);
+    delete x;
+    cudaGetLastError();
+    return set_error(code, msg);
+  };
   if (c->n_ranks > 1)
     {
-      // exchange the IPC handles with an NCCL all-gather of bytes
-      cudaIpcMemHandle_t mine;
-      SPIRK_CUDA(cudaIpcGetMemHandle(&mine, x->local));
       char *d_h = nullptr;
-      SPIRK_CUDA(cudaMalloc(&d_h, sizeof(mine) * (c->n_ranks + 1)));
-      SPIRK_CUDA(cudaMemcpyAsync(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
-      SPIRK_NCCL(nccl.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), ncclChar, c->comm, ctx->stream));
-      std::vector<cudaIpcMemHandle_t> all(c->n_ranks);
-      SPIRK_CUDA(cudaMemcpyAsync(all.data(), d_h + sizeof(mine), sizeof(mine) * c->n_ranks, cudaMemcpyDeviceToHost, ctx->stream));
-      SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
-      SPIRK_CUDA(cudaFree(d_h));
+      if (cudaMalloc(&d_h, sizeof(Packet) * (c->n_ranks + 1)) != cudaSuccess)
+        return fail(SPIRK_ERR_NOMEM, "xbuf: cudaMalloc of the handle exchange buffer failed (the other ranks may hang)");
+      std::vector<Packet> all(c->n_ranks);
+      const NcclApi      &api = nccl_api();
+      bool                comm_ok = api.ok;
+      comm_ok = comm_ok && cudaMemcpyAsync(d_h, &mine, sizeof(Packet), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
+      comm_ok = comm_ok && api.AllGather(d_h, d_h + sizeof(Packet), sizeof(Packet), ncclChar, c->comm, ctx->stream) == ncclSuccess;
+      comm_ok = comm_ok && cudaMemcpyAsync(all.data(), d_h + sizeof(Packet), sizeof(Packet) * c->n_ranks, cudaMemcpyDeviceToHost,
+                                           ctx->stream) == cudaSuccess;
+      comm_ok = comm_ok && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+      cudaFree(d_h);
+      if (!comm_ok)
+        return fail(SPIRK_ERR_COMM, "xbuf: exchange of the IPC handles failed");
+      for (int r = 0; r < c->n_ranks; ++r)
+        if (!all[r].ok)
+          return fail(SPIRK_ERR_DEVICE, r == c->rank ? "xbuf: " + why : "xbuf: rank " + std::to_string(r) + " could not create its buffer");
       for (int r = 0; r < c->n_ranks; ++r)
         if (r != c->rank)
           {
             void *p = nullptr;
-            SPIRK_CUDA(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+            if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+              return fail(SPIRK_ERR_DEVICE, "xbuf: cudaIpcOpenMemHandle failed (no peer access to rank " + std::to_string(r) + ")");
             x->peer[r] = (double *)p;
           }
     }
+  else if (!ok)
+    return fail(SPIRK_ERR_DEVICE, "xbuf: " + why);
   *out = x;
   return SPIRK_OK;
 }
@@ -1004,21 +1149,66 @@ int spirk_comm_xbuf_destroy(spirk_ctx *ctx, spirk_xbuf *x)
     return SPIRK_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int r = 0; r < x->n_ranks; ++r)
-    if (r != x->rank && x->peer[r])
-      cudaIpcCloseMemHandle(x->peer[r]);
+  if (!x->is_virtual)
+    for (int r = 0; r < x->n_ranks; ++r)
+      if (r != x->rank && x->peer[r])
+        cudaIpcCloseMemHandle(x->peer[r]);
   cudaFree(x->local);
-  cudaFree(x->d_sync);
+  if (x->d_sync)
+    cudaFree(x->d_sync);
   delete x;
   return SPIRK_OK;
 }
 
 double *spirk_comm_xbuf_local(spirk_xbuf *x) { return x->local; }
 
+int spirk_xbuf_create_virtual_group(spirk_ctx *ctx, int n_ranks, long long n, spirk_xbuf **out)
+{
+  if (n_ranks < 1 || n_ranks > SPIRK_MAX_BLOCKS || n < 1)
+    return set_error(SPIRK_ERR_INVALID, "xbuf virtual group: n_ranks / n");
+  SPIRK_CUDA(cudaSetDevice(ctx->device));
+  std::vector<spirk_xbuf *> xs(n_ranks, nullptr);
+  for (int r = 0; r < n_ranks; ++r)
+    {
+      spirk_xbuf *x = new spirk_xbuf();
+      x->n = n, x->rank = r, x->n_ranks = n_ranks, x->is_virtual = true;
+      if (cudaMalloc(&x->local, (size_t)2 * n * sizeof(double)) != cudaSuccess)
+        {
+          cudaGetLastError();
+          delete x;
+          for (spirk_xbuf *y : xs)
+            if (y)
+              cudaFree(y->local), delete y;
+          return set_error(SPIRK_ERR_NOMEM, "xbuf virtual group: cudaMalloc failed");
+        }
+      cudaMemsetAsync(x->local, 0, (size_t)2 * n * sizeof(double), ctx->stream);
+      xs[r] = x;
+    }
+  for (int r = 0; r < n_ranks; ++r)
+    {
+      xs[r]->peer.resize(n_ranks);
+      for (int j = 0; j < n_ranks; ++j)
+        xs[r]->peer[j] = xs[j]->local;
+      out[r] = xs[r];
+    }
+  return SPIRK_OK;
+}
+
+// stream-ordered barrier over the ranks of the exchange group (a 1-double all-reduce); none for a same-device
+// virtual group, whose "ranks" are ordered by the single stream they share
+static int xbuf_barrier(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x)
+{
+  if (c != nullptr && c->n_ranks > 1)
+    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  return SPIRK_OK;
+}
+
 int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, double *dst, long long ds, long long n,
                    const double *T, int add, double cutoff)
 {
-  const int qi = c->n_ranks * m;
+  if (c != nullptr && (c->n_ranks != x->n_ranks || c->rank != x->rank))
+    return set_error(SPIRK_ERR_INVALID, "mix_peer: communicator and exchange buffer do not match");
+  const int qi = x->n_ranks * m;
   if (qo < 1 || qi > SPIRK_MAX_BLOCKS || qo > SPIRK_MAX_BLOCKS || (long long)m * n > x->n)
     return set_error(SPIRK_ERR_INVALID, "mix_peer: block counts / buffer size");
   MixMatrix M;
@@ -1026,11 +1216,11 @@ int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, 
     for (int j = 0; j < qi; ++j)
       M.T[i * qi + j] = (std::fabs(T[i * qi + j]) > cutoff) ? T[i * qi + j] : 0.0;
   PeerPtrs pp;
-  for (int r = 0; r < c->n_ranks; ++r)
+  for (int r = 0; r < x->n_ranks; ++r)
     pp.p[r] = x->peer[r];
-  // stream-ordered rank barrier: every rank has finished writing its exchange buffer
-  if (c->n_ranks > 1)
-    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  // every rank has finished writing its exchange buffer
+  if (int e = xbuf_barrier(ctx, c, x))
+    return e;
   const int grid = grid_for(ctx, n, 256);
 #define MIXP_CASE(Q) \
   case Q: k_mix_peer<Q><<<grid, 256, 0, ctx->stream>>>(qo, m, dst, ds, pp, n, M, add); break;
@@ -1041,15 +1231,12 @@ int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, 
     }
   SPIRK_LAUNCH_CHECK(ctx);
   // ... and every rank has finished reading before a buffer may be overwritten
-  if (c->n_ranks > 1)
-    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
-  return SPIRK_OK;
+  return xbuf_barrier(ctx, c, x);
 }
 
-int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, double *dst, long long ds, long long n,
-                       const double *T, int add, double cutoff)
+int spirk_mix_peer_a2a_contract(spirk_ctx *ctx, spirk_xbuf *x, int m, long long n, const double *T, double cutoff)
 {
-  const int q = c->n_ranks * m;
+  const int q = x->n_ranks * m;
   if (m < 1 || q > SPIRK_MAX_BLOCKS || (long long)m * n > x->n)
     return set_error(SPIRK_ERR_INVALID, "mix_peer_a2a: block counts / buffer size");
   MixMatrix M;
@@ -1057,14 +1244,11 @@ int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, doub
     for (int j = 0; j < q; ++j)
       M.T[i * q + j] = (std::fabs(T[i * q + j]) > cutoff) ? T[i * q + j] : 0.0;
   PeerPtrsRW pp;
-  for (int r = 0; r < c->n_ranks; ++r)
+  for (int r = 0; r < x->n_ranks; ++r)
     pp.p[r] = x->peer[r];
   // this rank's chunk of every block
-  const long long e0 = n * c->rank / c->n_ranks, e1 = n * (c->rank + 1) / c->n_ranks;
-  // stream-ordered rank barrier: every rank has published its blocks (and is done with the previous results)
-  if (c->n_ranks > 1)
-    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
-  const int grid = grid_for(ctx, e1 - e0, 256);
+  const long long e0 = n * x->rank / x->n_ranks, e1 = n * (x->rank + 1) / x->n_ranks;
+  const int       grid = grid_for(ctx, e1 - e0, 256);
 #define MIXA_CASE(Q) \
   case Q: k_mix_a2a<Q><<<grid, 256, 0, ctx->stream>>>(m, pp, n, x->n, e0, e1, M); break;
   switch (q)
@@ -1073,12 +1257,32 @@ int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, doub
       MIXA_CASE(9) MIXA_CASE(10) MIXA_CASE(11) MIXA_CASE(12) MIXA_CASE(13) MIXA_CASE(14) MIXA_CASE(15) MIXA_CASE(16)
     }
   SPIRK_LAUNCH_CHECK(ctx);
-  // ... and every rank's result chunks have landed here
-  if (c->n_ranks > 1)
-    SPIRK_NCCL(nccl.AllReduce(x->d_sync, x->d_sync, 1, ncclDouble, ncclSum, c->comm, ctx->stream));
+  return SPIRK_OK;
+}
+
+int spirk_mix_peer_a2a_finish(spirk_ctx *ctx, spirk_xbuf *x, int m, double *dst, long long ds, long long n, int add)
+{
+  if (m < 1 || (long long)m * n > x->n)
+    return set_error(SPIRK_ERR_INVALID, "mix_peer_a2a: block counts / buffer size");
   k_mix_finish<<<grid_for(ctx, n * m, 256), 256, 0, ctx->stream>>>(m, dst, ds, x->local + x->n, n, add);
   SPIRK_LAUNCH_CHECK(ctx);
   return SPIRK_OK;
+}
+
+int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, double *dst, long long ds, long long n,
+                       const double *T, int add, double cutoff)
+{
+  if (c == nullptr || c->n_ranks != x->n_ranks || c->rank != x->rank)
+    return set_error(SPIRK_ERR_INVALID, "mix_peer_a2a: communicator and exchange buffer do not match");
+  // every rank has published its blocks (and is done with the previous results)
+  if (int e = xbuf_barrier(ctx, c, x))
+    return e;
+  if (int e = spirk_mix_peer_a2a_contract(ctx, x, m, n, T, cutoff))
+    return e;
+  // ... and every rank's result chunks have landed here
+  if (int e = xbuf_barrier(ctx, c, x))
+    return e;
+  return spirk_mix_peer_a2a_finish(ctx, x, m, dst, ds, n, add);
 }
 
 int spirk_ctx_set_reduction_comm(spirk_ctx *ctx, spirk_comm *comm)

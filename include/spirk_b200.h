@@ -226,6 +226,16 @@ int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *comm, spirk_xbuf *xbuf, int q_out
  * doubles cross NVLink per rank instead of (R-1) m n. */
 int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *comm, spirk_xbuf *xbuf, int m_per_rank, double *dst, long long dst_stride,
                        long long n, const double *host_T, int add, double cutoff);
+/* The two halves of spirk_mix_peer_a2a without the rank barriers (the caller orders them): contract = this rank's chunk of
+ * every block for all q outputs, written into the owners' result regions; finish = dst_i = [dst_i +] result_i. */
+int spirk_mix_peer_a2a_contract(spirk_ctx *ctx, spirk_xbuf *xbuf, int m_per_rank, long long n, const double *host_T, double cutoff);
+int spirk_mix_peer_a2a_finish(spirk_ctx *ctx, spirk_xbuf *xbuf, int m_per_rank, double *dst, long long dst_stride, long long n,
+                              int add);
+/* R exchange buffers on ONE device that see each other as peers: the ranks of a stage group emulated on a single GPU
+ * (B200_PROFILING.md: with fewer GPUs than ranks, run all ranks' data through the same kernels on one device).  Used by
+ * the single-GPU tests of the peer mixing kernels and by `spirk` runs with more stage ranks than devices; pass
+ * comm == NULL to spirk_mix_peer (rank and group size are the buffer's; stream order replaces the rank barrier). */
+int spirk_xbuf_create_virtual_group(spirk_ctx *ctx, int n_ranks, long long n, spirk_xbuf **xbufs /* n_ranks entries */);
 /* attach / detach (NULL) the communicator over which dot products are summed */
 int spirk_ctx_set_reduction_comm(spirk_ctx *ctx, spirk_comm *comm);
 

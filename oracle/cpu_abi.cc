@@ -1066,12 +1066,31 @@ int spirk_comm_allgather(spirk_ctx *, spirk_comm *c, double *recv, const double 
 }
 struct spirk_xbuf
 {
-  std::vector<double> local;
+  std::vector<double>       local; // [0, n): published blocks, [n, 2n): result region (all-to-all)
+  long long                 n = 0;
+  int                       rank = 0, n_ranks = 1;
+  std::vector<spirk_xbuf *> group; // same-process virtual group (spirk_xbuf_create_virtual_group)
 };
-int spirk_comm_xbuf_create(spirk_ctx *, spirk_comm *, long long n, spirk_xbuf **out)
+int spirk_comm_xbuf_create(spirk_ctx *, spirk_comm *c, long long n, spirk_xbuf **out)
 {
   *out = new spirk_xbuf();
-  (*out)->local.assign((size_t)n, 0.0);
+  (*out)->local.assign((size_t)2 * n, 0.0);
+  (*out)->n = n, (*out)->rank = c->rank, (*out)->n_ranks = c->n_ranks;
+  return SPIRK_OK;
+}
+int spirk_xbuf_create_virtual_group(spirk_ctx *, int n_ranks, long long n, spirk_xbuf **out)
+{
+  if (n_ranks < 1 || n_ranks > SPIRK_MAX_BLOCKS || n < 1)
+    return fail(SPIRK_ERR_INVALID, "xbuf virtual group: n_ranks / n");
+  std::vector<spirk_xbuf *> xs(n_ranks);
+  for (int r = 0; r < n_ranks; ++r)
+    {
+      xs[r] = new spirk_xbuf();
+      xs[r]->local.assign((size_t)2 * n, 0.0);
+      xs[r]->n = n, xs[r]->rank = r, xs[r]->n_ranks = n_ranks;
+    }
+  for (int r = 0; r < n_ranks; ++r)
+    xs[r]->group = xs, out[r] = xs[r];
   return SPIRK_OK;
 }
 int spirk_comm_xbuf_destroy(spirk_ctx *, spirk_xbuf *x)
@@ -1080,20 +1099,58 @@ int spirk_comm_xbuf_destroy(spirk_ctx *, spirk_xbuf *x)
   return SPIRK_OK;
 }
 double *spirk_comm_xbuf_local(spirk_xbuf *x) { return x->local.data(); }
-// the CPU double has no peer memory: all-gather through the registered callback, then mix locally
+// the blocks of all ranks, gathered: through the registered callback (real ranks) or from the virtual group
+static int xbuf_gather(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, long long n, std::vector<double> &all)
+{
+  all.assign((size_t)x->n_ranks * m * n, 0.0);
+  if (!x->group.empty())
+    {
+      for (int r = 0; r < x->n_ranks; ++r)
+        std::memcpy(&all[(size_t)r * m * n], x->group[r]->local.data(), (size_t)m * n * sizeof(double));
+      return SPIRK_OK;
+    }
+  if (!c)
+    return fail(SPIRK_ERR_INVALID, "mix_peer: a communicator is needed unless the buffer belongs to a virtual group");
+  std::vector<double> mine(x->local.begin(), x->local.begin() + (size_t)m * n);
+  return spirk_comm_allgather(ctx, c, all.data(), mine.data(), (long long)m * n);
+}
+// the CPU double has no peer memory: gather, then mix locally
 int spirk_mix_peer(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int qo, int m, double *dst, long long ds, long long n,
                    const double *T, int add, double cutoff)
 {
-  const int           qi = c->n_ranks * m;
-  std::vector<double> all((size_t)qi * n);
-  std::vector<double> mine((size_t)m * n);
-  for (int b = 0; b < m; ++b)
-    std::memcpy(&mine[(size_t)b * n], &x->local[(size_t)b * n], n * sizeof(double));
-  if (int e = spirk_comm_allgather(ctx, c, all.data(), mine.data(), (long long)m * n))
+  const int           qi = x->n_ranks * m;
+  std::vector<double> all;
+  if (int e = xbuf_gather(ctx, c, x, m, n, all))
     return e;
   return spirk_mix(ctx, qo, qi, dst, ds, all.data(), n, n, T, add, cutoff);
 }
-// all-to-all formulation: the same result; the CPU double gathers and mixes this rank's rows
+// all-to-all formulation, virtual groups only (real ranks use spirk_mix_peer_a2a): this rank's chunk of every block for all
+// q outputs, written into the owners' result regions
+int spirk_mix_peer_a2a_contract(spirk_ctx *ctx, spirk_xbuf *x, int m, long long n, const double *T, double cutoff)
+{
+  if (x->group.empty())
+    return fail(SPIRK_ERR_UNSUPPORTED, "mix_peer_a2a_contract: the CPU double supports it for virtual groups only");
+  const int       q  = x->n_ranks * m;
+  const long long e0 = n * x->rank / x->n_ranks, e1 = n * (x->rank + 1) / x->n_ranks;
+  for (int i = 0; i < q; ++i)
+    for (long long e = e0; e < e1; ++e)
+      {
+        double t = 0.0;
+        for (int j = 0; j < q; ++j)
+          if (std::fabs(T[i * q + j]) > cutoff)
+            t += T[i * q + j] * x->group[j / m]->local[(size_t)(j % m) * n + e];
+        x->group[i / m]->local[(size_t)x->n + (size_t)(i % m) * n + e] = t;
+      }
+  (void)ctx;
+  return SPIRK_OK;
+}
+int spirk_mix_peer_a2a_finish(spirk_ctx *, spirk_xbuf *x, int m, double *dst, long long ds, long long n, int add)
+{
+  for (int i = 0; i < m; ++i)
+    for (long long e = 0; e < n; ++e)
+      dst[i * ds + e] = (add ? dst[i * ds + e] : 0.0) + x->local[(size_t)x->n + (size_t)i * n + e];
+  return SPIRK_OK;
+}
 int spirk_mix_peer_a2a(spirk_ctx *ctx, spirk_comm *c, spirk_xbuf *x, int m, double *dst, long long ds, long long n, const double *T,
                        int add, double cutoff)
 {

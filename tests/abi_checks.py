@@ -42,7 +42,13 @@ def block_input(olv, nb, seed=0, zero_boundary=False):
     return u
 
 
-def check_op_apply(dev, dim, k, r, desc, tol=RTOL):
+def set_options(ctx, opts):
+    """spirk_ctx_set_option knobs (include/spirk_b200.h) for A/B tests of the kernel variants / schedules"""
+    for name, value in (opts or {}).items():
+        ctx.call("spirk_ctx_set_option", name.encode(), int(value))
+
+
+def check_op_apply(dev, dim, k, r, desc, tol=RTOL, opts=None):
     """desc: ('real', mass[], lap[]) or ('coupled', C[][], lap[])."""
     lvl, olv = make_level(dim, k, r)
     if desc[0] == "real":
@@ -65,6 +71,7 @@ def check_op_apply(dev, dim, k, r, desc, tol=RTOL):
         ref = Kv + np.tensordot(Cm, Mv, axes=(1, 0))
         ref[:, olv.bmask] = u[:, olv.bmask]
     with capi.Context(dev) as ctx:
+        set_options(ctx, opts)
         src = ctx.upload(u)
         dst = ctx.alloc(u.size)
         ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), dst, src, olv.N)
@@ -122,6 +129,71 @@ def check_residual_and_cheb(dev, dim, k, r, nb=2):
         # x_new aliasing x_old (how the smoother calls it)
         ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dxo, dx, dxo, db, None, olv.N, pf1, pf2)
         assert relerr(ctx.download(dxo, x.shape), ref) < RTOL
+
+
+_FULL_CACHE = {}
+
+
+def full_size_case(r, nb):
+    """oracle data of the 3-D Q4 fused-kernel checks at refinement r (cached: the Kronecker oracle costs seconds at r = 6)"""
+    key = (r, nb)
+    if key not in _FULL_CACHE:
+        _, olv = make_level(3, 4, r)
+        mass = np.array(D4[:nb])
+        lap = np.full(nb, 0.1)
+        x = block_input(olv, nb, 3, True)
+        xo = block_input(olv, nb, 4, True)
+        b = block_input(olv, nb, 5, True)
+        bb = block_input(olv, nb, 6, False)
+        dinv = np.concatenate([olv.inverse_diagonal(m, 0.1) for m in mass])
+        f0, f1, f2 = np.array([0.7, 0.6, 0.65, 0.75][:nb]), np.array([0.3, 0.2, 0.25, 0.35][:nb]), np.array([1.1, 0.9, 1.0, 1.2][:nb])
+        bc = (slice(None),) + (None,) * 3
+        Ax = olv.apply(x, mass, lap)
+        x1 = f0[bc] * dinv * bb
+        x2 = x1 + f1[bc] * x1 + f2[bc] * dinv * (bb - olv.apply(x1, mass, lap))
+        _FULL_CACHE[key] = dict(olv=olv, mass=mass, lap=lap, x=x, xo=xo, b=b, bb=bb, dinv=dinv, f0=f0, f1=f1, f2=f2, Ax=Ax,
+                                res=b - Ax, cheb=x + f1[bc] * (x - xo) + f2[bc] * dinv * (b - Ax),
+                                cheb0=(1 + f1[bc]) * x + f2[bc] * dinv * (b - Ax), x1=x1, x2=x2)
+    return _FULL_CACHE[key]
+
+
+def check_v3_full_size(dev, r, nb, opts=None, tol=RTOL):
+    """Every mode of the plane-streaming cell operator the solver launches (apply, residual, Chebyshev step with explicit /
+    on-the-fly inverse diagonal, x_old = 0, x_new aliasing x_old, the fused first two iterations) at a BASELINE-size level
+    (r = 5: 2.1e6, r = 6: 1.7e7 DoFs per block) against the Kronecker oracle, under the given schedule / thread-layout options."""
+    c = full_size_case(r, nb)
+    olv, N = c["olv"], c["olv"].N
+    lvl = capi.Level(3, 4, 2 ** r, 0)
+    op = capi.real_op(c["mass"], c["lap"])
+    errs = {}
+    with capi.Context(dev) as ctx:
+        set_options(ctx, opts)
+        dx, dxo, db, dd, dbb = (ctx.upload(c[k]) for k in ("x", "xo", "b", "dinv", "bb"))
+        d1, d2 = ctx.alloc(nb * N), ctx.alloc(nb * N)
+        shape = c["x"].shape
+        pf0, _0 = capi.darr(c["f0"])
+        pf1, _1 = capi.darr(c["f1"])
+        pf2, _2 = capi.darr(c["f2"])
+        ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), d1, dx, N)
+        errs["apply"] = relerr(ctx.download(d1, shape), c["Ax"])
+        ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), d2, dx, N)
+        assert np.array_equal(ctx.download(d1, shape), ctx.download(d2, shape)), "the fast path must be bitwise reproducible"
+        ctx.call("spirk_op_residual", C.byref(lvl), C.byref(op), d1, db, dx, N)
+        errs["residual"] = relerr(ctx.download(d1, shape), c["res"])
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), d1, dx, dxo, db, dd, N, pf1, pf2)
+        errs["cheb_dinv"] = relerr(ctx.download(d1, shape), c["cheb"])
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), d1, dx, dxo, db, None, N, pf1, pf2)
+        errs["cheb_own"] = relerr(ctx.download(d1, shape), c["cheb"])
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), d1, dx, None, db, None, N, pf1, pf2)
+        errs["cheb_own_x0"] = relerr(ctx.download(d1, shape), c["cheb0"])
+        ctx.call("spirk_op_cheb_first", C.byref(lvl), C.byref(op), d1, d2, dbb, N, pf0, pf1, pf2)
+        errs["cheb_first_x1"] = relerr(ctx.download(d1, shape), c["x1"])
+        errs["cheb_first_x2"] = relerr(ctx.download(d2, shape), c["x2"])
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dxo, dx, dxo, db, None, N, pf1, pf2)  # x_new aliases x_old
+        errs["cheb_own_alias"] = relerr(ctx.download(dxo, shape), c["cheb"])
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, f"r={r} nb={nb} opts={opts}: {bad}"
+    return errs
 
 
 def check_inverse_diagonal(dev, dim, k, r, mass=16.0, lap=0.1):
@@ -239,6 +311,48 @@ def check_mix(dev, q=4, n=20011):
         du = ctx.upload(dst0[0])
         ctx.call("spirk_mix", 1, q, du, n, ds, n, n, pb, 1, 0.0)
         assert relerr(ctx.download(du, (n,)), dst0[0] + 0.1 * (b @ src)) < 1e-13
+
+
+def check_mix_peer_virtual(dev, R, m, n=30011):
+    """spirk_mix_peer (gather formulation) and spirk_mix_peer_a2a_contract / _finish (all-to-all formulation) with the R
+    ranks of a stage group emulated on one device (spirk_xbuf_create_virtual_group): every rank's result must equal its
+    rows of the plain mixing so.mix (reference perform_basis_change, main.cc:1486-1534, incl. the 1e-12 cut-off)."""
+    q = R * m
+    rng = np.random.default_rng(q)
+    T = so.table("T_inv", q) if 2 <= q <= 10 else rng.standard_normal((q, q))
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    src = synth(q * n, 7).reshape(q, n)      # block j lives on rank j // m
+    dst0 = synth(q * n, 8).reshape(q, n)
+    ref = so.mix(T, src)
+    with capi.Context(dev) as ctx:
+        xs = (C.c_void_p * R)()
+        ctx.call("spirk_xbuf_create_virtual_group", R, m * n, xs)
+        try:
+            for r in range(R):
+                loc = C.c_void_p(dev.lib.spirk_comm_xbuf_local(xs[r]))
+                ctx.call("spirk_copy_h2d", loc, np.ascontiguousarray(src[r * m:(r + 1) * m]).ctypes.data_as(C.c_void_p), m * n)
+            for add in (0, 1):
+                # gather formulation: rank r contracts all q blocks for its m rows
+                for r in range(R):
+                    d = ctx.upload(dst0[r * m:(r + 1) * m])
+                    rows, _k = capi.darr(T[r * m:(r + 1) * m])
+                    ctx.call("spirk_mix_peer", None, xs[r], m, m, d, n, n, rows, add, 1e-12)
+                    want = ref[r * m:(r + 1) * m] + (dst0[r * m:(r + 1) * m] if add else 0.0)
+                    assert relerr(ctx.download(d, (m, n)), want) < 1e-13, (R, m, r, add, "gather")
+                    ctx.free(d)
+                # all-to-all formulation: every rank contracts its chunk for all outputs, then every rank collects
+                full, _f = capi.darr(T)
+                for r in range(R):
+                    ctx.call("spirk_mix_peer_a2a_contract", xs[r], m, n, full, 1e-12)
+                for r in range(R):
+                    d = ctx.upload(dst0[r * m:(r + 1) * m])
+                    ctx.call("spirk_mix_peer_a2a_finish", xs[r], m, d, n, n, add)
+                    want = ref[r * m:(r + 1) * m] + (dst0[r * m:(r + 1) * m] if add else 0.0)
+                    assert relerr(ctx.download(d, (m, n)), want) < 1e-13, (R, m, r, add, "a2a")
+                    ctx.free(d)
+        finally:
+            for r in range(R):
+                ctx.call("spirk_comm_xbuf_destroy", xs[r])
 
 
 def check_problem(dev, dim, k, r):

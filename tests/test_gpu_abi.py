@@ -93,3 +93,22 @@ def test_vector_kernels(gpu_dev):
     ac.check_mix(gpu_dev)
     ac.check_mix(gpu_dev, q=8)
     ac.check_dense_matvec(gpu_dev)
+
+
+# every k_v3<K, TX, TY, MODE, NPT, NBC> instantiation v3_launch can select, at the sizes the bench runs (r = 5, 6): the
+# 8 x 8-cell tiles with NPT = 4 (apply) and NPT = 2 (fused epilogues, and apply under v3_npt = 2), nb in {1, 2}, even-split
+# and z-lockstep schedules; the 4 x 4-cell instantiations are the r <= 4 cases above
+@pytest.mark.parametrize("r,nb,opts", [
+    (5, 1, {"v3_schedule": 0}), (5, 1, {"v3_schedule": 1}), (5, 2, {"v3_schedule": 0, "v3_npt": 2}),
+    (5, 2, {"v3_schedule": 1, "v3_npt": 4}), (5, 2, {}), (6, 2, {}), (6, 1, {"v3_schedule": 0}), (6, 2, {"v3_schedule": 1, "v3_npt": 2}),
+    (5, 2, {"v3_small_below": 64}),  # 4 x 4-cell tiles at r = 5
+])
+def test_v3_all_modes_full_size(gpu_dev, r, nb, opts):
+    ac.check_v3_full_size(gpu_dev, r, nb, opts)
+
+
+@pytest.mark.parametrize("r,opts", [(5, {}), (5, {"v3_schedule": 1}), (6, {}), (5, {"v3_small_below": 64})])
+def test_v3_coupled_pair_full_size(gpu_dev, r, opts):
+    """k_v3<..., APPLY, 4, NBC = 2>: complex pair and the IRK q = 2 system matrix (main.cc:1014-1028) at bench size"""
+    ac.check_op_apply(gpu_dev, 3, 4, r, ac.OP_CASES[4], opts=opts)
+    ac.check_op_apply(gpu_dev, 3, 4, r, ("coupled", ac.so.table("A_inv", 2).tolist(), [0.1]), opts=opts)

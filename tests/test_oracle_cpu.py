@@ -116,3 +116,10 @@ def test_host_library_exports_every_symbol():
     assert len(declared) >= 18
     for name in declared:
         assert hasattr(lib, name), name
+
+
+def test_cpu_double_virtual_rank_mixing(cpu_dev):
+    """the same check the -m gpu suite runs on the peer mixing kernels, here on the CPU double (host-side logic of the test)"""
+    import abi_checks as ac
+    ac.check_mix_peer_virtual(cpu_dev, 2, 1, n=2003)
+    ac.check_mix_peer_virtual(cpu_dev, 4, 2, n=1001)
