@@ -4,9 +4,12 @@
 A "step" is one fully implicit Runge-Kutta time step of the 3-D Q4 heat equation (rhs assembly,
 GMG-preconditioned GMRES on the stage system, solution update).
 
-  N = 1 : BASELINE.json configs[1]: 3-D Q4, IRK q=2, GMG preconditioner, single B200
-  N > 1 : stage-parallel SPIRK with q = N stages, one Radau-IIA stage per GPU (configs[2] at N=4,
-          configs[4]'s q=8 at N=8), NCCL all-gather stage mixing + all-reduced Krylov scalars.
+  N = 1 : BASELINE.json configs[1]: 3-D Q4, IRK q=2, GMG preconditioner, single B200.  The line also carries
+          `scaling_reference`: the N>1 workload (spirk q=8) run on this one GPU with all 8 stages batched, the N=1 point of
+          the strong-scaling series below.
+  N > 1 : stage-parallel SPIRK with a FIXED q = 8 stages (configs[4]'s scheme at r=6), q/N stages per GPU: a strong-scaling
+          series over N = 1, 2, 4, 8 (the outer iteration count depends on q, so only a fixed q makes the per-N values
+          comparable); fused peer-memory stage mixing + all-reduced Krylov scalars.
 
 metric  : stage-DoFs advanced per second = n_dofs * q / (time per step)   [GDoF*stage/s];
           ms_per_step is the time per SPIRK step; the roofline object reports the dominant kernel
@@ -42,7 +45,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--refine", type=int, default=6, help="global refinements r: n_dofs = (4*2^r+1)^3")
     ap.add_argument("--degree", type=int, default=4)
-    ap.add_argument("--stages", type=int, default=0, help="RK stages q (default: 2 at N=1, N otherwise)")
+    ap.add_argument("--stages", type=int, default=0, help="RK stages q (default: 2 at N=1, 8 otherwise)")
+    ap.add_argument("--no-scaling-reference", action="store_true", help="N=1: skip the spirk q=8 run on one GPU")
     ap.add_argument("--scheme", default="", help="irk | spirk | irk_batched | complex_* (default irk at N=1, spirk else)")
     ap.add_argument("--outer-tolerance", type=float, default=1e-8, help="reference default main.cc:2964")
     ap.add_argument("--cpu-refine-min", type=int, default=4, help="smallest refinement of the bounded CPU sample")
@@ -176,7 +180,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = a.gpus
-    q = a.stages or (2 if n_gpus == 1 else n_gpus)
+    q = a.stages or (2 if n_gpus == 1 else 8)
+    if q % n_gpus:
+        raise SystemExit(f"--stages {q} must be a multiple of --gpus {n_gpus}")
     scheme = a.scheme or ("irk" if n_gpus == 1 else "spirk")
     metric = "implicit RK time step: stage-DoFs advanced per second (n_dofs*q/step time); ms_per_step = time per SPIRK step"
     unit = "GDoF*stage/s"
@@ -329,17 +335,40 @@ def main():
         # x_new = 32 B (D^-1 is formed on the fly, A x never reaches memory); plain vmult reads src, writes dst = 16 B
         cheb_gbs = 32.0 * m * N / res["cheb_step"] * 1e-6
         vmult_gdofs = m * N / res["vmult"] * 1e-6
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath):  # measured DRAM bytes / algorithmic bytes of this kernel (ncu --set full capture)
-            traffic = json.load(open(tpath))["traffic_over_algorithmic"] * 32.0 * m * N
+        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture (profiles/), scaled to this launch's
+        # algorithmic bytes; NOT measured in this run (bench numbers are never taken under a profiler)
+        traffic, traffic_src = None, None
+        for name in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath))["traffic_over_algorithmic"] * 32.0 * m * N
+                traffic_src = "profiles/" + name
+                break
         roof = {"bound": "hbm", "kernel": "fused Chebyshev step (cell operator + 3-term update), the smoother's kernel",
                 "achieved": cheb_gbs, "peak": peak, "unit": "GB/s", "frac": cheb_gbs / peak, "traffic": traffic,
-                "traffic_note": "bytes per launch = (dram read+write)/algorithmic ratio of the ncu capture in profiles/ x this launch's algorithmic bytes",
+                "traffic_source": traffic_src,
+                "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture (ratio to algorithmic bytes x this launch's algorithmic bytes); not re-measured in this run",
                 "peak_source": peak_src, "algorithmic_bytes_per_dof": 32, "launch_ms": res["cheb_step"],
                 "vmult": {"achieved": 16.0 * vmult_gdofs, "frac": 16.0 * vmult_gdofs / peak, "launch_ms": res["vmult"],
                           "algorithmic_bytes_per_dof": 16}}
     run.close()
+
+    # ---- N = 1 point of the strong-scaling series: the N > 1 workload (spirk, q = 8) with all stages batched on this GPU
+    scaling_ref = None
+    if n_gpus == 1 and not a.no_scaling_reference and not a.stages and not a.scheme:
+        qs, ns = 8, max(2, min(a.steps, 4))
+        with hostapi.Run(host, params("spirk", a.degree, a.refine, qs, a.outer_tolerance, ns + 3), dim=3, device=local_rank) as r8:
+            r8.setup()
+            r8.set_compute_errors(False)
+            for _ in range(2):
+                r8.step()
+            r8.timer_begin()
+            for _ in range(ns):
+                r8.step()
+            ms8 = r8.timer_end() / ns
+            scaling_ref = {"workload": f"3D heat equation Q{a.degree}, spirk q={qs}, hypercube r={a.refine}, all {qs} stages batched on 1 GPU",
+                           "stages": qs, "steps": ns, "ms_per_step": ms8, "value": n_dofs * qs / ms8 * 1e-6, "unit": unit,
+                           "outer_iterations": [int(x) for x in r8.array("outer_iterations")[-ns:]]}
 
     cpu = None
     if rank == 0 and n_gpus == 1 and not a.no_cpu_baseline:
@@ -357,13 +386,13 @@ def main():
     if rank == 0:
         value = n_dofs * q / t_step * 1e-9
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": n_gpus, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak" if n_gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "clocks": clocks,
                 "e2e": {"value": n_dofs * q / t_e2e * 1e-9, "unit": unit, "ms_per_step": t_e2e * 1e3,
                         "h2d_bytes_per_step": int(n_dofs * 8), "d2h_bytes_per_step": int(n_dofs * 8)},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "vmult_gdofs": vmult_gdofs,
                 "outer_iterations": [int(x) for x in outer], "step_ms_host_clock": [round(s * 1e3, 3) for s in step_seconds], "wall_ms_per_step": wall / a.steps * 1e3,
-                "error_L2_t0": float(err0[0]), "error_L2_final": float(err_final)}
+                "error_L2_t0": float(err0[0]), "error_L2_final": float(err_final), "scaling_reference": scaling_ref}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -76,6 +76,7 @@ _SIGS = {
     "spirk_malloc_host": [C.c_void_p, C.POINTER(C.c_void_p), C.c_size_t],
     "spirk_free_host": [C.c_void_p, C.c_void_p],
     "spirk_op_apply": [C.c_void_p, C.POINTER(Level), C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_longlong],
+    "spirk_op_apply_km": [C.c_void_p, C.POINTER(Level), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, dp, dp],
     "spirk_op_residual": [C.c_void_p, C.POINTER(Level), C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_void_p,
                           C.c_longlong],
     "spirk_op_cheb_step": [C.c_void_p, C.POINTER(Level), C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_void_p,

@@ -182,8 +182,10 @@ namespace spirk
     int       ncc;           // coarse cells along d
     long long N_out, N_in;   // entries per block
   };
+  // restriction along y or z (d = 1, 2): one thread per output entry, lanes along x (coalesced loads and stores);
+  // grid.x covers one output xy-plane, grid.y = (output z) x (vector block)
   template <int K>
-  __global__ void __launch_bounds__(256) k_restrict_1d(const Sweep1D w, const int nb, double *__restrict__ out, const long long os,
+  __global__ void __launch_bounds__(256) k_restrict_1d(const Sweep1D w, double *__restrict__ out, const long long os,
                                                        const double *__restrict__ in, const long long is)
   {
     constexpr int n = K + 1;
@@ -191,46 +193,102 @@ namespace spirk
     for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
       P[t] = c_fe[K].P[t];
     __syncthreads();
-    SPIRK_GRID_STRIDE(e, w.N_out * nb)
-    {
-      const int       b  = (int)(e / w.N_out);
-      const long long r  = e - b * w.N_out;
-      const int       ox = (int)(r % w.ex), oy = (int)((r / w.ex) % w.ey), oz = (int)(r / ((long long)w.ex * w.ey));
-      const int       i  = (w.d == 0) ? ox : (w.d == 1 ? oy : oz); // coarse index along d
-      const int       n1c = K * w.ncc + 1;
-      double          s  = 0.0;
-      if (i > 0 && i < n1c - 1) // coarse Dirichlet entries stay 0
-        {
-          // input strides: the input has extent n_in along d, the output's extents elsewhere
-          const long long sx = 1, sy = (w.d == 0) ? w.n_in : w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
-          const long long sd = (w.d == 0) ? sx : (w.d == 1 ? sy : sz);
-          const long long base = b * is + ((w.d == 0) ? 0 : ox) + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz);
-          const int       ec = i / K, il = i - ec * K;
-          if (il != 0)
-            {
-              const double *p = in + base + (long long)(2 * K * ec) * sd;
+    const unsigned pxy = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pxy >= (unsigned)(w.ex * w.ey))
+      return;
+    const int ox = pxy % (unsigned)w.ex, oy = pxy / (unsigned)w.ex;
+    const int oz = blockIdx.y % (unsigned)w.ez, b = blockIdx.y / (unsigned)w.ez;
+    const int i  = (w.d == 1) ? oy : oz; // coarse index along d
+    const int n1c = K * w.ncc + 1;
+    double    s  = 0.0;
+    if (i > 0 && i < n1c - 1) // coarse Dirichlet entries stay 0
+      {
+        // the input has extent n_in along d and the output's extents elsewhere
+        const long long sy = w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
+        const long long sd = (w.d == 1) ? sy : sz;
+        const int       ec = i / K, il = i - ec * K;
+        const double   *p  = in + b * is + ox + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz) + (long long)(2 * K * ec) * sd;
+        if (il != 0)
+          {
 #pragma unroll
-              for (int jl = 0; jl <= 2 * K; ++jl)
-                s = fma(P[jl * n + il], p[jl * sd], s);
-            }
-          else
-            {
-              // vertex node of the coarse mesh: the fine nodes of both adjacent coarse cells (the shared one once)
-              const double *p = in + base + (long long)(2 * K * ec) * sd;
-              s               = p[0];
+            for (int jl = 0; jl <= 2 * K; ++jl)
+              s = fma(P[jl * n + il], p[jl * sd], s);
+          }
+        else
+          {
+            // vertex node of the coarse mesh: the fine nodes of both adjacent coarse cells (the shared one once)
+            s = p[0];
 #pragma unroll
-              for (int jl = 1; jl <= 2 * K; ++jl)
-                s = fma(P[jl * n + 0], p[jl * sd], s);
+            for (int jl = 1; jl <= 2 * K; ++jl)
+              s = fma(P[jl * n + 0], p[jl * sd], s);
 #pragma unroll
-              for (int jl = 0; jl < 2 * K; ++jl)
-                s = fma(P[jl * n + K], p[(jl - 2 * K) * sd], s);
-            }
-        }
-      out[b * os + r] = s;
-    }
+            for (int jl = 0; jl < 2 * K; ++jl)
+              s = fma(P[jl * n + K], p[(jl - 2 * K) * sd], s);
+          }
+      }
+    out[b * os + ox + (long long)w.ex * (oy + (long long)w.ey * oz)] = s;
   }
-  template <int K, bool ADD>
-  __global__ void __launch_bounds__(256) k_prolongate_1d(const Sweep1D w, const int nb, double *__restrict__ out, const long long os,
+  // restriction along x: a block stages RPB fine rows in shared memory (coalesced), every thread contracts from there
+  template <int K, int RPB>
+  __global__ void __launch_bounds__(256) k_restrict_x(const int n1f, const int ncc, const long long rows, const long long rows_per_block,
+                                                      double *__restrict__ out, const long long os, const double *__restrict__ in,
+                                                      const long long is)
+  {
+    constexpr int n = K + 1;
+    extern __shared__ double srow[]; // RPB rows of n1f entries, then P
+    double       *P   = srow + (size_t)RPB * n1f;
+    const int     n1c = K * ncc + 1;
+    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
+      P[t] = c_fe[K].P[t];
+    __shared__ long long off_in[RPB], off_out[RPB]; // row offsets (64-bit divisions once per row, not per entry)
+    for (long long r0 = (long long)blockIdx.x * RPB; r0 < rows; r0 += (long long)gridDim.x * RPB)
+      {
+        __syncthreads();
+        const int nr = (int)min((long long)RPB, rows - r0);
+        if (threadIdx.x < nr)
+          {
+            const long long R = r0 + threadIdx.x, b = R / rows_per_block, rl = R - b * rows_per_block;
+            off_in[threadIdx.x] = b * is + rl * n1f, off_out[threadIdx.x] = b * os + rl * n1c;
+          }
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr * n1f; t += blockDim.x)
+          {
+            const int rr = t / n1f, x = t - rr * n1f;
+            srow[t]      = in[off_in[rr] + x];
+          }
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr * n1c; t += blockDim.x)
+          {
+            const int rr = t / n1c, i = t - rr * n1c;
+            double    s  = 0.0;
+            if (i > 0 && i < n1c - 1)
+              {
+                const int     ec = i / K, il = i - ec * K;
+                const double *p  = srow + rr * n1f + 2 * K * ec;
+                if (il != 0)
+                  {
+#pragma unroll
+                    for (int jl = 0; jl <= 2 * K; ++jl)
+                      s = fma(P[jl * n + il], p[jl], s);
+                  }
+                else
+                  {
+                    s = p[0];
+#pragma unroll
+                    for (int jl = 1; jl <= 2 * K; ++jl)
+                      s = fma(P[jl * n + 0], p[jl], s);
+#pragma unroll
+                    for (int jl = 0; jl < 2 * K; ++jl)
+                      s = fma(P[jl * n + K], p[jl - 2 * K], s);
+                  }
+              }
+            out[off_out[rr] + i] = s;
+          }
+      }
+  }
+  // prolongation along y or z: one thread per output entry, lanes along x
+  template <int K>
+  __global__ void __launch_bounds__(256) k_prolongate_1d(const Sweep1D w, double *__restrict__ out, const long long os,
                                                          const double *__restrict__ in, const long long is)
   {
     constexpr int n = K + 1;
@@ -238,31 +296,68 @@ namespace spirk
     for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
       P[t] = c_fe[K].P[t];
     __syncthreads();
-    SPIRK_GRID_STRIDE(e, w.N_out * nb)
-    {
-      const int       b  = (int)(e / w.N_out);
-      const long long r  = e - b * w.N_out;
-      const int       ox = (int)(r % w.ex), oy = (int)((r / w.ex) % w.ey), oz = (int)(r / ((long long)w.ex * w.ey));
-      const int       j  = (w.d == 0) ? ox : (w.d == 1 ? oy : oz); // fine index along d
-      const long long sx = 1, sy = (w.d == 0) ? w.n_in : w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
-      const long long sd = (w.d == 0) ? sx : (w.d == 1 ? sy : sz);
-      const long long base = b * is + ((w.d == 0) ? 0 : ox) + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz);
-      const int       ec = min(j / (2 * K), w.ncc - 1), jl = j - 2 * K * ec;
-      const int       n1c = K * w.ncc + 1;
-      const double   *p  = in + base + (long long)(K * ec) * sd;
-      double          s  = 0.0;
+    const unsigned pxy = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pxy >= (unsigned)(w.ex * w.ey))
+      return;
+    const int       ox = pxy % (unsigned)w.ex, oy = pxy / (unsigned)w.ex;
+    const int       oz = blockIdx.y % (unsigned)w.ez, b = blockIdx.y / (unsigned)w.ez;
+    const int       j  = (w.d == 1) ? oy : oz; // fine index along d
+    const long long sy = w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
+    const long long sd = (w.d == 1) ? sy : sz;
+    const int       ec = min(j / (2 * K), w.ncc - 1), jl = j - 2 * K * ec;
+    const int       n1c = K * w.ncc + 1;
+    const double   *p  = in + b * is + ox + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz) + (long long)(K * ec) * sd;
+    double          s  = 0.0;
 #pragma unroll
-      for (int il = 0; il <= K; ++il)
-        {
-          const int i = K * ec + il;
-          if (i > 0 && i < n1c - 1) // coarse Dirichlet entries are read as 0
-            s = fma(P[jl * n + il], p[il * sd], s);
-        }
-      if (ADD)
-        out[b * os + r] += s;
-      else
-        out[b * os + r] = s;
-    }
+    for (int il = 0; il <= K; ++il)
+      {
+        const int i = K * ec + il;
+        if (i > 0 && i < n1c - 1) // coarse Dirichlet entries are read as 0
+          s = fma(P[jl * n + il], p[il * sd], s);
+      }
+    out[b * os + ox + (long long)w.ex * (oy + (long long)w.ey * oz)] = s;
+  }
+  // prolongation along x, added into the fine vector: RPB coarse rows staged in shared memory per block
+  template <int K, int RPB>
+  __global__ void __launch_bounds__(256) k_prolongate_x_add(const int n1f, const int ncc, const long long rows, const long long rows_per_block,
+                                                            double *__restrict__ out, const long long os, const double *__restrict__ in,
+                                                            const long long is)
+  {
+    constexpr int n = K + 1;
+    extern __shared__ double srow[]; // RPB rows of n1c entries, then P
+    const int     n1c = K * ncc + 1;
+    double       *P   = srow + (size_t)RPB * n1c;
+    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
+      P[t] = c_fe[K].P[t];
+    __shared__ long long off_in[RPB], off_out[RPB];
+    for (long long r0 = (long long)blockIdx.x * RPB; r0 < rows; r0 += (long long)gridDim.x * RPB)
+      {
+        __syncthreads();
+        const int nr = (int)min((long long)RPB, rows - r0);
+        if (threadIdx.x < nr)
+          {
+            const long long R = r0 + threadIdx.x, b = R / rows_per_block, rl = R - b * rows_per_block;
+            off_in[threadIdx.x] = b * is + rl * n1c, off_out[threadIdx.x] = b * os + rl * n1f;
+          }
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr * n1c; t += blockDim.x)
+          {
+            const int rr = t / n1c, i = t - rr * n1c;
+            srow[t]      = (i > 0 && i < n1c - 1) ? in[off_in[rr] + i] : 0.0; // Dirichlet: 0
+          }
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr * n1f; t += blockDim.x)
+          {
+            const int     rr = t / n1f, j = t - rr * n1f;
+            const int     ec = min(j / (2 * K), ncc - 1), jl = j - 2 * K * ec;
+            const double *p  = srow + rr * n1c + K * ec;
+            double        s  = 0.0;
+#pragma unroll
+            for (int il = 0; il <= K; ++il)
+              s = fma(P[jl * n + il], p[il], s);
+            out[off_out[rr] + j] += s;
+          }
+      }
   }
 
   // y_b = A x_b, tiny dense (coarse-grid solve): one block per vector block
@@ -364,6 +459,22 @@ namespace spirk
                                                       const long long n, double *partials)
   {
     double s = 0.0;
+    SPIRK_GRID_STRIDE(i, n)
+    {
+      const double t = fma(a, V[i], v[i]);
+      const double w = (W == v) ? t : W[i];
+      v[i]           = t;
+      s              = fma(t, w, s);
+    }
+    block_reduce_store<RT>(s, partials + blockIdx.x);
+  }
+  // the same with the coefficient read from device memory, negated: v -= (*coef) V (the Gram-Schmidt sweep keeps its
+  // scalars on the device, so a sweep needs one host synchronisation instead of one per basis vector)
+  __global__ void __launch_bounds__(RT) k_sub_and_dot_dev(double *v, const double *__restrict__ coef, const double *__restrict__ V,
+                                                          const double *W, const long long n, double *partials)
+  {
+    const double a = -(*coef);
+    double       s = 0.0;
     SPIRK_GRID_STRIDE(i, n)
     {
       const double t = fma(a, V[i], v[i]);
@@ -498,6 +609,19 @@ namespace spirk
       if (g.dim == 3)
         v *= t1[iz];
       out[i] = (zero_bdry && bd) ? 0.0 : v;
+    }
+  }
+
+  // y_b += x_b on interior DoFs (the Dirichlet rows of y keep their values)
+  __global__ void k_add_interior(const Geo g, const int nb, double *y, const long long ys, const double *__restrict__ x, const long long xs)
+  {
+    SPIRK_GRID_STRIDE(e, g.N * nb)
+    {
+      const int       b  = e / g.N;
+      const long long i  = e - b * g.N;
+      const int       ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? i / ((long long)g.n1 * g.n1) : 1;
+      if (!(on_bdry(ix, g.n1) || on_bdry(iy, g.n1) || (g.dim == 3 && on_bdry(iz, g.n1))))
+        y[b * ys + i] += x[b * xs + i];
     }
   }
 

@@ -142,15 +142,17 @@ namespace spirk
     double        cc[16]; // coupled operators (<= 4 blocks): coupling * h^3, row-major; V2_CHEB_FIRST: f0 of the blocks
                           // (x1 = f0 dinv src; x1 is written to the `dinv` pointer, which that mode does not read)
     int           coupled;
+    int           km; // coupled pair whose second input is block b of ANOTHER vector (map tm_o0): dst_b = cl_b K u_b + cc[2b+1] M w_b
     int           ntx, nty;
     long long     W; // nb * columns * layers
     int           lock_nch, lock_len; // > 0: z-lockstep schedule (CTA = one column x one of lock_nch equal layer ranges)
-    // dyn != 0: work-item schedule.  Items = (block, layer range of lock_len layers, column), dealt round robin to the CTAs in
+    // dyn != 0: work-queue schedule.  Items = (block, layer range of lock_len layers, column), drawn from an atomic counter in
     // that order (concurrent CTAs work on neighbouring columns at similar heights); a range that starts above layer 0 does
     // NOT recompute the layer below: the two CTAs that meet at a range boundary exchange the partial z-sums of the shared
     // vertex plane through `carry` (whoever is ready first publishes, the other one adds and stores; a + b is commutative,
     // so the result is bitwise reproducible)
     int           dyn, n_items;
+    int          *sched;  // [0] next item, [1] CTAs that are done (the last one resets both)
     int          *state;  // per range boundary: 0 idle, 1 claimed by the first arrival, 2 its partial sums are published
     double       *carry;  // per range boundary: OX * OY partial sums
     long long     rows_per_block; // stride / n1: the blocks continue the row sequence of block 0
@@ -222,7 +224,7 @@ namespace spirk
     double   *sm3  = sm3_raw + (((128u - (smem_u32(sm3_raw) & 127u)) & 127u) >> 3); // TMA boxes: 128-byte aligned
     double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K, *SD1 = SDI + K * K * K;
     uint64_t *BAR  = reinterpret_cast<uint64_t *>(SD1 + K * K * K);
-    int      *QS   = reinterpret_cast<int *>(BAR + NBUF); // [2] role at a range boundary
+    int      *QS   = reinterpret_cast<int *>(BAR + NBUF); // [0] drawn item, [2] role at a range boundary
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
     const double  Mv = c_fe[K].Mv;
 #define MC(i, j) Mh[v3_canon<K>(i, j)]
@@ -259,20 +261,21 @@ namespace spirk
       }
     int             b_tab = -1;
     unsigned        it0   = 0; // ring position of the piece's first plane (runs on across pieces)
-    int             q_item = (int)blockIdx.x;
     for (;;)
       {
         // ------------------------------------------------------------------ next piece: block b, column col, layers [L0, L1)
         int L0, L1, col, b;
         if (a.dyn)
           {
-            // items are dealt round robin (item = blockIdx.x + n gridDim.x: block-uniform, so everything derived from it
-            // lives in uniform registers; an atomic draw from a queue would cost ~25 vector registers per thread)
+            // items are drawn from a queue (measured against dealing them round robin: 17 - 20 % faster at r = 6, 7; the
+            // CTAs of one SM do not progress at the same rate)
             __syncthreads(); // the previous piece is finished (ring, a'/c tile, tables, QS)
-            if (q_item >= a.n_items)
+            if (tid == 0)
+              QS[0] = atomicAdd(a.sched, 1);
+            __syncthreads();
+            const int item = QS[0];
+            if (item >= a.n_items)
               break;
-            const int item = q_item;
-            q_item += (int)gridDim.x;
             col            = item % ncols;
             const int rest = item / ncols, ch = rest % a.lock_nch;
             b              = rest / a.lock_nch;
@@ -346,9 +349,12 @@ namespace spirk
                   for (int j = 0; j < NBC; ++j)
                     {
                       // coupled: the plane of every block (block j starts rows_per_block * (j - b) rows away)
-                      const long long Rj = (NBC == 1) ? Rb : Rb + (long long)(j - b) * a.rows_per_block;
-                      tma_g2s_2d(dst + j * (2 * UB * 8), &a.tm_src, (gx0 - K + a.sh_src) & ~1, (int)((Rj + 1) >> 1), bar);
-                      tma_g2s_2d(dst + j * (2 * UB * 8) + UB * 8, &a.tm_src, (n1 + gx0 - K + a.sh_src) & ~1, (int)(Rj >> 1), bar);
+                      const bool         second = (NBC > 1) && a.km && (j == 1); // the plane of w_b (same rows as u_b)
+                      const long long    Rj  = (NBC == 1 || a.km) ? Rb : Rb + (long long)(j - b) * a.rows_per_block;
+                      const CUtensorMap *tm  = second ? &a.tm_o0 : &a.tm_src;
+                      const int          shj = second ? a.sh_o0 : a.sh_src;
+                      tma_g2s_2d(dst + j * (2 * UB * 8), tm, (gx0 - K + shj) & ~1, (int)((Rj + 1) >> 1), bar);
+                      tma_g2s_2d(dst + j * (2 * UB * 8) + UB * 8, tm, (n1 + gx0 - K + shj) & ~1, (int)(Rj >> 1), bar);
                     }
                 }
               if (owned)
@@ -390,9 +396,9 @@ namespace spirk
         // shared-memory offset of staged row r / operand row ro of a plane whose staged row 0 has parity par_: box of the
         // row's parity, position inside the box, and the 8-byte parity of the row start (a box starts at the 16-byte
         // aligned element at or below the first wanted one; gx0, K even, n1 odd)
-        auto urow = [&](const int r, const int par_) {
+        auto urow = [&](const int r, const int par_, const int sh = -1) {
           const int blk = (par_ + r) & 1;
-          return blk * UB + ((r - (par_ ^ blk)) >> 1) * BW + (a.sh_src ^ blk);
+          return blk * UB + ((r - (par_ ^ blk)) >> 1) * BW + ((sh < 0 ? a.sh_src : sh) ^ blk);
         };
         auto orow = [&](const int ro, const int par_, const int sh) {
           const int blk = (par_ + ro) & 1; // K is even: operand row 0 (= staged row K) has the parity of staged row 0
@@ -480,8 +486,9 @@ namespace spirk
                     for (int jb = 0; jb < NBC; ++jb)
                       {
                         // coupled: block jb's staged plane (its row parity differs by the parity of the block distance)
-                        const int     pj = (NBC == 1) ? xpar : (xpar ^ (((jb - b) & 1) & (int)(a.rows_per_block & 1)));
-                        const double *ur = xub + jb * (2 * UB) + urow(row, pj) + K * seg;
+                        // (km: staged plane 0 = u_b, plane 1 = w_b, both at the rows of block b)
+                        const int     pj = (NBC == 1 || a.km) ? xpar : (xpar ^ (((jb - b) & 1) & (int)(a.rows_per_block & 1)));
+                        const double *ur = xub + jb * (2 * UB) + urow(row, pj, (a.km && jb == 1) ? a.sh_o0 : a.sh_src) + K * seg;
                         double        u[2 * K + 1];
 #pragma unroll
                         for (int j = 0; j < 2 * K + 1; ++j)
@@ -530,12 +537,12 @@ namespace spirk
                           }
                         if (NBC > 1)
                           {
-                            const double cbj = a.cc[b * NBC + jb];
+                            const double cbj = a.cc[(b * NBC + jb) % 16];
 #pragma unroll
                             for (int i = 0; i < K; ++i)
                               cmix[i] = fma(cbj, mj[i], cmix[i]);
                           }
-                        if (NBC == 1 || jb == b)
+                        if (NBC == 1 || jb == (a.km ? 0 : b))
                           {
                             // stiffness sweep (K' for plain operators) of the block this CTA produces
 #pragma unroll
@@ -913,6 +920,11 @@ namespace spirk
               v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % oxe) + (long long)n1 * (gy0 + e / oxe) + plane * (n1 - 1), f0);
           }
       }
+    if (a.dyn && tid == 0 && atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1)
+      {
+        a.sched[0] = 0, a.sched[1] = 0; // the last CTA out: every other CTA has drawn its final (out of range) item
+        __threadfence();
+      }
 #undef MC
 #undef KC
   }
@@ -994,6 +1006,9 @@ namespace spirk
     if (int e = v3_make_map(&a.tm_src, &a.sh_src, a.src, n_elems, a.g.n1, C::BW, C::BH, l2p))
       return e;
     a.tm_o0 = a.tm_src, a.tm_o1 = a.tm_src, a.sh_o0 = a.sh_o1 = 0;
+    if (NBC > 1 && a.km) // the second staged plane comes from block b of the vector passed as x_old
+      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, a.x_old, n_elems, a.g.n1, C::BW, C::BH, l2p))
+        return e;
     const double *o0 = (MODE == V2_RESIDUAL) ? a.rhs : (MODE == V2_CHEB_OWN ? a.x_old : nullptr);
     if (o0 != nullptr)
       if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, o0, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
@@ -1001,13 +1016,13 @@ namespace spirk
     if (MODE == V2_CHEB_OWN)
       if (int e = v3_make_map(&a.tm_o1, &a.sh_o1, a.rhs, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
         return e;
-    // Schedules (option "v3_schedule"): 2 (default) (block, layer range, column) items dealt round robin, with the partial sums
+    // Schedules (option "v3_schedule"): 2 (default) work queue of (block, layer range, column) items with the partial sums
     // of the shared vertex planes exchanged between neighbouring ranges (no recomputation, any number of items per CTA);
     // 0 even static split of the (block, column, layer) space, 1 z-lockstep (one column x one of nch equal layer ranges per
     // CTA) - in both a piece that starts above layer 0 recomputes the layer below it.
     const long long slots = (long long)ctx->n_sms * C::MINB;
     long long       grid  = std::max(1LL, std::min(ctx->opt_v3_grid > 0 ? (long long)ctx->opt_v3_grid : slots, a.W / 4));
-    a.lock_nch = 0, a.lock_len = 0, a.dyn = 0, a.n_items = 0, a.state = nullptr, a.carry = nullptr;
+    a.lock_nch = 0, a.lock_len = 0, a.dyn = 0, a.n_items = 0, a.sched = nullptr, a.state = nullptr, a.carry = nullptr;
     const long long cols  = (long long)a.nb * a.ntx * a.nty;
     const int       force = ctx->opt_v3_schedule;
     if (force < 0 || force == 2)
@@ -1030,7 +1045,7 @@ namespace spirk
         a.n_items  = (int)(cols * a.lock_nch);
         if (int e = ensure_v3_queue(ctx, (size_t)a.n_items, (size_t)a.n_items * C::NY * NPT))
           return e;
-        a.state = ctx->d_v3_sched, a.carry = ctx->d_v3_carry;
+        a.sched = ctx->d_v3_sched, a.state = ctx->d_v3_sched + 4, a.carry = ctx->d_v3_carry;
         grid    = std::max(1LL, std::min(ctx->opt_v3_grid > 0 ? (long long)ctx->opt_v3_grid : slots, (long long)a.n_items));
       }
     else if (ctx->opt_v3_grid <= 0)
@@ -1102,7 +1117,7 @@ namespace spirk
     if (op->nb > 1 && stride % g.n1 != 0)
       return SPIRK_ERR_UNSUPPORTED; // the blocks must continue the row sequence of block 0 (one tensor map)
     V3Args a;
-    a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1, a.coupled = coupled ? 1 : 0;
+    a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1, a.coupled = coupled ? 1 : 0, a.km = 0;
     a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = (mode == V2_CHEB_FIRST) ? dst1 : dinv;
     if (mode == V2_CHEB_FIRST && (coupled || f0 == nullptr || dst1 == nullptr || dst1 == dst || dst1 == src))
       return SPIRK_ERR_UNSUPPORTED;
@@ -1139,10 +1154,40 @@ namespace spirk
       return v3_launch<4, 4, 4, 4>(ctx, a, mode);
     // nodes per y+z thread on the 8 x 8 tile: 4 = 20 warps/SM at 96 registers, 2 = 32 warps/SM at 64 registers (some
     // spills); measured: 4 is better for the plain apply at r = 6, 2 for the fused epilogues
-    const int npt = (ctx->opt_v3_npt == 2 || ctx->opt_v3_npt == 4) ? ctx->opt_v3_npt : (mode == V2_APPLY ? 4 : 2);
+    // measured with the work-queue schedule (r = 6, nb = 2): apply 0.275 ms with 2 nodes per thread, 0.308 ms with 4
+    const int npt = (ctx->opt_v3_npt == 2 || ctx->opt_v3_npt == 4) ? ctx->opt_v3_npt : 2;
     if (npt == 2)
       return v3_launch<4, 8, 8, 2>(ctx, a, mode);
     return v3_launch<4, 8, 8, 4>(ctx, a, mode);
+  }
+
+  // dst_b = laplace[b] K v_b + mass[b] M w_b for nb blocks of two block vectors with the same stride, in ONE pass over the
+  // cells (24 B per DoF: v and w read, dst written) - the stage-parallel system matrix after the A_inv mixing of the
+  // source, main.cc:1580-1592 (M commutes with the stage mixing).  Dirichlet rows: dst_b = v_b.
+  inline int v3_apply_km(spirk_ctx *ctx, const Geo &g, const int nb, double *dst, const double *v, const double *w, const long long stride,
+                         const double *laplace, const double *mass)
+  {
+    if (g.dim != 3 || g.k != 4 || g.nc % 4 != 0 || g.nc < 8 || nb < 1 || nb > 8 || stride % g.n1 != 0)
+      return SPIRK_ERR_UNSUPPORTED;
+    V3Args a;
+    a.g = g, a.nb = nb, a.stride = stride, a.rows_per_block = stride / g.n1, a.coupled = 1, a.km = 1;
+    a.dst = dst, a.src = v, a.x_old = w, a.rhs = nullptr, a.dinv = nullptr;
+    const double hd = g.h * g.h * g.h, hl = g.h;
+    constexpr int K = 4, n = K + 1;
+    double        Ms[n * n], Ks[n * n];
+    fe_host_sym(K, Ms, Ks);
+    for (int b = 0; b < nb; ++b)
+      {
+        a.cm[b] = 0.0, a.cl[b] = laplace[b] * hl, a.f1[b] = a.f2[b] = 0.0, a.sc[b] = 1.0;
+        for (int i = 0; i < n; ++i)
+          for (int j = 0; j < n; ++j)
+            a.kp[b][v3_cidx<K>(i, j)] = Ks[i * n + j];
+        a.kp[b][V3_NKP - 1] = a.kp[b][v3_cidx<K>(K, K)] + a.kp[b][v3_cidx<K>(0, 0)];
+        a.cc[2 * b] = 0.0, a.cc[2 * b + 1] = mass[b] * hd;
+      }
+    if (g.nc % 8 != 0 || g.nc < ctx->opt_v3_small_below)
+      return v3_launch<4, 4, 4, 4>(ctx, a, V2_APPLY);
+    return v3_launch<4, 8, 8, 4>(ctx, a, V2_APPLY);
   }
 #endif // SPIRK_V3_INSTANTIATE
 } // namespace spirk

@@ -508,6 +508,37 @@ int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *o
   return apply_any(ctx, g, op, dst, src, stride);
 }
 
+int spirk_op_apply_km(spirk_ctx *ctx, const spirk_level *lvl, int nb, double *dst, const double *v, const double *w, long long stride,
+                      const double *laplace, const double *mass)
+{
+  if (int e = check_level(lvl))
+    return e;
+  if (nb < 1 || nb > SPIRK_MAX_BLOCKS || dst == v || dst == w)
+    return set_error(SPIRK_ERR_INVALID, "op_apply_km: block count / aliasing");
+  const Geo g = make_geo(lvl);
+  if (ctx->opt_apply_variant == 0)
+    {
+      int st = v3_apply_km(ctx, g, nb, dst, v, w, stride, laplace, mass);
+      if (st != SPIRK_ERR_UNSUPPORTED)
+        return st;
+    }
+  // general path: dst = laplace K v, scratch = mass M w, dst += scratch (Dirichlet rows: dst = v)
+  spirk_opdesc dk, dm;
+  std::memset(&dk, 0, sizeof(dk)), std::memset(&dm, 0, sizeof(dm));
+  dk.kind = dm.kind = SPIRK_OP_REAL, dk.nb = dm.nb = nb;
+  for (int b = 0; b < nb; ++b)
+    dk.laplace[b] = laplace[b], dm.mass[b] = mass[b];
+  if (int e = spirk_op_apply(ctx, lvl, &dk, dst, v, stride))
+    return e;
+  if (int e = ensure_scratch(ctx, (size_t)stride * nb)) // (one stride for source and destination blocks)
+    return e;
+  if (int e = spirk_op_apply(ctx, lvl, &dm, ctx->d_scratch, w, stride))
+    return e;
+  k_add_interior<<<grid_for(ctx, g.N * nb, 256), 256, 0, ctx->stream>>>(g, nb, dst, stride, ctx->d_scratch, stride);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return SPIRK_OK;
+}
+
 int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst, const double *rhs,
                       const double *src, long long stride)
 {
@@ -683,29 +714,36 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
       SPIRK_LAUNCH_CHECK(ctx);
       return SPIRK_OK;
     }
-  // expand z, then y, then x (adding into the fine vector)
+  // expand z, then y (one thread per entry, lanes along x), then x from rows staged in shared memory, adding into the fine vector
+  constexpr int RPB = 8;
+  const auto grid_1d = [&](const Sweep1D &w) { return dim3((unsigned)((w.ex * w.ey + 255) / 256), (unsigned)(w.ez * nb)); };
+  const size_t    smem_x = sizeof(double) * ((size_t)RPB * ncn + (2 * g.k + 1) * (g.k + 1));
   if (g.dim == 3)
     {
-      const Sweep1D   wz = make_sweep(2, ncn, ncn, nf, ncn, ncc), wy = make_sweep(1, ncn, nf, nf, ncn, ncc), wx = make_sweep(0, nf, nf, nf, ncn, ncc);
+      const Sweep1D wz = make_sweep(2, ncn, ncn, nf, ncn, ncc), wy = make_sweep(1, ncn, nf, nf, ncn, ncc);
       if (int e = ensure_scratch(ctx, (size_t)nb * (wz.N_out + wy.N_out)))
         return e;
       double *t2 = ctx->d_scratch, *t1 = ctx->d_scratch + (size_t)nb * wz.N_out;
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, false><<<grid_for(ctx, wz.N_out * nb, 256), 256, 0, ctx->stream>>>(wz, nb, t2, wz.N_out, coarse, cs)));
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wz), 256, 0, ctx->stream>>>(wz, t2, wz.N_out, coarse, cs)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, false><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, t1, wy.N_out, t2, wz.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, t2, wz.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, true><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, fine, fs, t1, wy.N_out)));
+      const long long rpb = (long long)nf * nf, rows = rpb * nb;
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+                              nf, ncc, rows, rpb, fine, fs, t1, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
   else
     {
-      const Sweep1D wy = make_sweep(1, ncn, nf, 1, ncn, ncc), wx = make_sweep(0, nf, nf, 1, ncn, ncc);
+      const Sweep1D wy = make_sweep(1, ncn, nf, 1, ncn, ncc);
       if (int e = ensure_scratch(ctx, (size_t)nb * wy.N_out))
         return e;
       double *t1 = ctx->d_scratch;
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, false><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, t1, wy.N_out, coarse, cs)));
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, coarse, cs)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K, true><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, fine, fs, t1, wy.N_out)));
+      const long long rpb = nf, rows = rpb * nb;
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+                              nf, ncc, rows, rpb, fine, fs, t1, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
   return SPIRK_OK;
@@ -741,18 +779,24 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
       SPIRK_LAUNCH_CHECK(ctx);
       return SPIRK_OK;
     }
-  // contract x, then y, then z: every coarse entry is written exactly once
+  // contract x (fine rows staged in shared memory), then y, then z (one thread per entry, lanes along x): every coarse
+  // entry is written exactly once
+  constexpr int RPB = 8;
+  const auto grid_1d = [&](const Sweep1D &w) { return dim3((unsigned)((w.ex * w.ey + 255) / 256), (unsigned)(w.ez * nb)); };
+  const size_t    smem_x = sizeof(double) * ((size_t)RPB * nf + (2 * g.k + 1) * (g.k + 1));
   if (g.dim == 3)
     {
       const Sweep1D wx = make_sweep(0, ncn, nf, nf, nf, ncc), wy = make_sweep(1, ncn, ncn, nf, nf, ncc), wz = make_sweep(2, ncn, ncn, ncn, nf, ncc);
       if (int e = ensure_scratch(ctx, (size_t)nb * (wx.N_out + wy.N_out)))
         return e;
-      double *t1 = ctx->d_scratch, *t2 = ctx->d_scratch + (size_t)nb * wx.N_out;
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, t1, wx.N_out, fine, fs)));
+      double         *t1 = ctx->d_scratch, *t2 = ctx->d_scratch + (size_t)nb * wx.N_out;
+      const long long rpb = (long long)nf * nf, rows = rpb * nb;
+      SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+                              nf, ncc, rows, rpb, t1, wx.N_out, fine, fs)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, t2, wy.N_out, t1, wx.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t2, wy.N_out, t1, wx.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wz.N_out * nb, 256), 256, 0, ctx->stream>>>(wz, nb, coarse, cs, t2, wy.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wz), 256, 0, ctx->stream>>>(wz, coarse, cs, t2, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
   else
@@ -760,10 +804,12 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
       const Sweep1D wx = make_sweep(0, ncn, nf, 1, nf, ncc), wy = make_sweep(1, ncn, ncn, 1, nf, ncc);
       if (int e = ensure_scratch(ctx, (size_t)nb * wx.N_out))
         return e;
-      double *t1 = ctx->d_scratch;
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wx.N_out * nb, 256), 256, 0, ctx->stream>>>(wx, nb, t1, wx.N_out, fine, fs)));
+      double         *t1 = ctx->d_scratch;
+      const long long rpb = nf, rows = rpb * nb;
+      SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+                              nf, ncc, rows, rpb, t1, wx.N_out, fine, fs)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_for(ctx, wy.N_out * nb, 256), 256, 0, ctx->stream>>>(wy, nb, coarse, cs, t1, wx.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, coarse, cs, t1, wx.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
   return SPIRK_OK;
@@ -869,17 +915,35 @@ int spirk_vec_sum(spirk_ctx *ctx, const double *x, long long n, double *host_res
 
 int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *const *basis, int dim, long long n, double *h, double *norm)
 {
-  if (dim < 1)
+  if (dim < 1 || dim > 62)
     return set_error(SPIRK_ERR_INVALID, "gmres_mgs: dim");
-  if (int e = spirk_vec_dot(ctx, vv, basis[0], n, &h[0]))
+  // h_i and the final norm stay in d_result[0 .. dim]; every update reads its coefficient from there (and, with a
+  // reduction communicator attached, after the stream-ordered all-reduce of that scalar): ONE host synchronisation per sweep
+  const int grid = reduction_grid(ctx, n);
+  auto      finish = [&](int slot) -> int {
+    k_finish<<<1, RT, 0, ctx->stream>>>(ctx->d_partials, grid, ctx->d_result + slot);
+    SPIRK_LAUNCH_CHECK(ctx);
+    if (ctx->reduction_comm)
+      return spirk_comm_allreduce_sum(ctx, ctx->reduction_comm, ctx->d_result + slot, 1);
+    return SPIRK_OK;
+  };
+  k_dot<<<grid, RT, 0, ctx->stream>>>(vv, basis[0], n, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  if (int e = finish(0))
     return e;
-  for (int i = 1; i < dim; ++i)
-    if (int e = spirk_vec_add_and_dot(ctx, vv, -h[i - 1], basis[i - 1], basis[i], n, &h[i]))
-      return e;
-  double s = 0;
-  if (int e = spirk_vec_add_and_dot(ctx, vv, -h[dim - 1], basis[dim - 1], vv, n, &s))
-    return e;
-  *norm = std::sqrt(s);
+  for (int i = 1; i <= dim; ++i)
+    {
+      k_sub_and_dot_dev<<<grid, RT, 0, ctx->stream>>>(vv, ctx->d_result + (i - 1), basis[i - 1], (i < dim) ? basis[i] : vv, n,
+                                                      ctx->d_partials);
+      SPIRK_LAUNCH_CHECK(ctx);
+      if (int e = finish(i))
+        return e;
+    }
+  SPIRK_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, (dim + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < dim; ++i)
+    h[i] = ctx->h_result[i];
+  *norm = std::sqrt(ctx->h_result[dim]);
   return SPIRK_OK;
 }
 

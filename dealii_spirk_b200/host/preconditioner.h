@@ -304,9 +304,25 @@ namespace spirk_host
                 else
                   {
                     check(st, "spirk_graph_begin");
-                    level_v_step(top);
-                    SPIRK_CHECK(spirk_graph_end(dev->ctx(), &graph));
-                    graph_descs = now;
+                    // whatever goes wrong inside the capture (a launch that cannot be captured, an allocation): end the
+                    // capture so that the stream is usable again, and run this and all later V-cycles eagerly
+                    bool captured = false;
+                    try
+                      {
+                        level_v_step(top);
+                        captured = true;
+                      }
+                    catch (const Error &)
+                      {}
+                    const int st_end = spirk_graph_end(dev->ctx(), &graph);
+                    if (captured && st_end == SPIRK_OK)
+                      graph_descs = now;
+                    else
+                      {
+                        if (st_end == SPIRK_OK && graph)
+                          spirk_graph_destroy(graph);
+                        graph = nullptr, graph_unsupported = true;
+                      }
                   }
               }
             if (graph)

@@ -12,7 +12,9 @@
 // A row communicator with P ranks owns q / P consecutive stages (resp. conjugate pairs) per rank, so
 // the same classes cover 1 GPU (all stages batched on one device) up to one stage per GPU.
 #pragma once
+#include <array>
 #include <chrono>
+#include <cmath>
 #include <cstdlib>
 #include <functional>
 #include <iostream>
@@ -60,6 +62,23 @@ namespace spirk_host
         if (size > 1)
           SPIRK_CHECK(spirk_comm_allreduce_sum(v.ctx(), comm, v.data(), v.size()));
       }
+      // {min, avg, max} over the ranks
+      std::array<double, 3> min_max_avg(Device &dev, const double x) const
+      {
+        if (size == 1)
+          return {{x, x, x}};
+        std::vector<double> mine(size, 0.0), all(size);
+        mine[rank] = x;
+        Vector t;
+        t.reinit(dev, size, 1, true);
+        t.copy_from_host(mine.data());
+        all_reduce_sum(t);
+        t.copy_to_host(all.data());
+        double mn = all[0], mx = all[0], s = 0;
+        for (const double v : all)
+          mn = std::min(mn, v), mx = std::max(mx, v), s += v;
+        return {{mn, s / size, mx}};
+      }
       double sum(Device &dev, double x) const
       {
         if (size == 1)
@@ -73,9 +92,22 @@ namespace spirk_host
       }
     };
 
-    inline double now_ns(const Vector &v)
+    // The reference's timers (main.cc:853-969) bracket finished work; kernels here are asynchronous.  The stamps at the
+    // beginning and the end of a step always synchronise (`boundary`); the fine-grained ones inside the Krylov loop do so
+    // only with SPIRK_SYNC_TIMERS=1 (they would otherwise cost several host-device round trips per GMRES iteration), so by
+    // default t_vmult / t_prec_bc / t_prec_solver measure the host's enqueue time and t / t_rhs / t_solver / t_update are exact.
+    inline bool sync_timers()
     {
-      v.device().sync(); // kernels are asynchronous; the reference's timers bracket finished work
+      static const bool v = [] {
+        const char *e = std::getenv("SPIRK_SYNC_TIMERS");
+        return e && std::atoi(e) != 0;
+      }();
+      return v;
+    }
+    inline double now_ns(const Vector &v, const bool boundary = false)
+    {
+      if (boundary || sync_timers())
+        v.device().sync();
       return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::system_clock::now().time_since_epoch()).count();
     }
 
@@ -163,13 +195,13 @@ namespace spirk_host
     public:
       void get_statistics(ConvergenceTable &table, const double scaling_factor = 1.0) const override
       {
-        // min/max/avg over the global communicator: identical on every rank of a row here
-        for (const char *s : {"n_outer_min", "n_outer_avg", "n_outer_max"})
-          table.add_value(s, n_outer_iterations / scaling_factor);
-        for (const char *s : {"n_inner_min", "n_inner_avg", "n_inner_max"})
-          table.add_value(s, n_inner_iterations / scaling_factor);
+        // Utilities::MPI::min_max_avg over the global communicator (main.cc:689-719): all-gather over the stage ranks
+        const auto mma = [&](const double value) { return stat_min_max_avg ? stat_min_max_avg(value) : std::array<double, 3>{{value, value, value}}; };
+        const auto o = mma(n_outer_iterations / scaling_factor), in = mma(n_inner_iterations / scaling_factor);
+        table.add_value("n_outer_min", o[0]), table.add_value("n_outer_avg", o[1]), table.add_value("n_outer_max", o[2]);
+        table.add_value("n_inner_min", in[0]), table.add_value("n_inner_avg", in[1]), table.add_value("n_inner_max", in[2]);
         const auto add_time = [&](const std::string label, const double value) {
-          table.add_value(label, value / 1e9);
+          table.add_value(label, mma(value)[1] / 1e9);
           table.set_scientific(label, true);
         };
         add_time("t", time_total);
@@ -180,6 +212,9 @@ namespace spirk_host
         add_time("t_prec_bc", time_preconditioner_bc);
         add_time("t_prec_solver", time_preconditioner_solver);
       }
+
+      // {min, avg, max} of a per-rank value over the ranks; set by the stage-parallel integrators (identity otherwise)
+      mutable std::function<std::array<double, 3>(double)> stat_min_max_avg;
 
       // per-step records (not in the reference's table; used by the parity tests and bench.py)
       mutable std::vector<unsigned int>              outer_iterations_per_step;
@@ -256,6 +291,11 @@ namespace spirk_host
         m_local = n_stages / row.size;
         s0      = row.rank * m_local;
       }
+      ~IRKGeneral() override
+      {
+        if (xbuf)
+          spirk_comm_xbuf_destroy(xbuf_ctx, xbuf); // the peer-mapped exchange buffer and the IPC mappings of the other ranks
+      }
 
       void get_statistics(ConvergenceTable &table, const double scaling_factor = 1.0) const override
       {
@@ -275,8 +315,14 @@ namespace spirk_host
         this->time_step = time_step;
         if (!preconditioner_ready)
           setup_preconditioner(solution);
+        if (row.size > 1 && !this->stat_min_max_avg)
+          {
+            Device *d = &solution.device();
+            const RowComm r = row;
+            this->stat_min_max_avg = [d, r](const double v) { return r.min_max_avg(*d, v); };
+          }
 
-        const double t_total = now_ns(solution);
+        const double t_total = now_ns(solution, true);
         Device      &dev     = solution.device();
         const long long N    = solution.size();
 
@@ -294,7 +340,7 @@ namespace spirk_host
           g.block(i).add(1.0, tmp);
         perform_basis_change(system_rhs, g, A_inv, false, 0.0);
 
-        const double t_solver = now_ns(solution);
+        const double t_solver = now_ns(solution, true);
         this->time_rhs += t_solver - t_total;
 
         ReductionControl solver_control(n_max_iterations, 1e-20, outer_tolerance);
@@ -310,15 +356,20 @@ namespace spirk_host
           {
             throw Error(e.what());
           }
-        const double t_update = now_ns(solution);
+        const double t_update = now_ns(solution, true);
         this->time_outer_solver += t_update - t_solver;
         this->n_outer_iterations += solver_control.last_step();
         outer_iterations_per_step.push_back(solver_control.last_step());
+        if (row.size > 1) // the counts of the stages owned by the other ranks (a stage is a rank of the reference's row communicator)
+          for (unsigned int i = 0; i < n_stages; ++i)
+            n_inner[i] = (unsigned int)std::lround(row.sum(dev, (i >= s0 && i < s0 + m_local) ? (double)n_inner[i] : 0.0));
         inner_iterations_per_step.push_back(n_inner);
         double inner_sum = 0;
         for (unsigned int i = 0; i < m_local; ++i)
           inner_sum += n_inner[s0 + i];
-        this->n_inner_iterations += (row.size == 1 ? inner_sum : n_inner[s0]);
+        // IRK: the sum over the stages (main.cc:936-943); IRKStageParallel: the count of this rank's stage (main.cc:1398-1401),
+        // here the mean over the local stages
+        this->n_inner_iterations += (row.size == 1 ? inner_sum : inner_sum / m_local);
 
         if (pcout)
           {
@@ -331,7 +382,14 @@ namespace spirk_host
                     *pcout << "+" << n_inner[i];
               }
             else
-              *pcout << n_inner[s0] << "/" << (double)n_inner[s0] << "/" << n_inner[s0];
+              {
+                // min / avg / max over the row communicator = over the stages (main.cc:1403-1411)
+                unsigned int mn = n_inner[0], mx = n_inner[0];
+                double       sum = 0;
+                for (unsigned int i = 0; i < n_stages; ++i)
+                  mn = std::min(mn, n_inner[i]), mx = std::max(mx, n_inner[i]), sum += n_inner[i];
+                *pcout << mn << "/" << sum / n_stages << "/" << mx;
+              }
             *pcout << " inner CG iterations." << std::endl;
           }
 
@@ -345,7 +403,7 @@ namespace spirk_host
           SPIRK_CHECK(spirk_mix(dev.ctx(), 1, m_local, solution.data(), N, system_solution.data(), N, N, w.data(), 1, 0.0));
           row.all_reduce_sum(solution);
         }
-        const double t_end = now_ns(solution);
+        const double t_end = now_ns(solution, true);
         this->time_solution_update += t_end - t_update;
         this->time_total += t_end - t_total;
         last_stage_solution = std::move(system_solution);
@@ -410,6 +468,7 @@ namespace spirk_host
             xbuf_a2a      = !(e && std::atoi(e) == 1); // SPIRK_PEER_MIX=1: gather formulation, default: all-to-all
             if (!(e && std::atoi(e) == 0))
               {
+                xbuf_ctx     = src.ctx();
                 const int st = spirk_comm_xbuf_create(src.ctx(), row.comm, src.block_size() * m_local, &xbuf);
                 // all ranks must agree (a rank without peer access falls back together with the others)
                 const double ok = row.sum(src.device(), st == SPIRK_OK ? 0.0 : 1.0);
@@ -425,6 +484,7 @@ namespace spirk_host
         return xbuf_state == 1;
       }
       mutable spirk_xbuf *xbuf       = nullptr;
+      mutable spirk_ctx  *xbuf_ctx   = nullptr;
       mutable int         xbuf_state = 0; // 0: not tried, 1: peer exchange, 2: NCCL all-gather
       mutable bool        xbuf_a2a   = true;
 
@@ -451,13 +511,13 @@ namespace spirk_host
             }
           else
             {
-              std::vector<double> zero(p.m_local, 0.0), one(p.m_local, 1.0), tau(p.m_local, p.time_step);
-              const spirk_opdesc  dk = real_opdesc(p.m_local, zero.data(), tau.data());
-              const spirk_opdesc  dm = real_opdesc(p.m_local, one.data(), zero.data());
+              // M commutes with the stage mixing: w = (A_inv (x) I) v first, then ONE cell pass dst = tau K v + M w
+              // (24 B per DoF) instead of the reference's K pass, M pass and mixing with add (main.cc:1582-1591)
+              std::vector<double> one(p.m_local, 1.0), tau(p.m_local, p.time_step);
               p.temp.reinit(src, true);
-              SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &dk, dst.data(), src.data(), src.block_size()));
-              SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &dm, p.temp.data(), src.data(), src.block_size()));
-              p.perform_basis_change(dst, p.temp, p.A_inv, true, 0.0);
+              p.perform_basis_change(p.temp, src, p.A_inv, false, 0.0);
+              SPIRK_CHECK(spirk_op_apply_km(src.ctx(), &mf.level, (int)p.m_local, dst.data(), src.data(), p.temp.data(),
+                                            src.block_size(), tau.data(), one.data()));
             }
           p.time_system_vmult += now_ns(src) - t0;
         }
@@ -684,7 +744,7 @@ namespace spirk_host
                 }
             }
 
-        const double    t_total = now_ns(solution);
+        const double    t_total = now_ns(solution, true);
         Device         &dev     = solution.device();
         const long long N       = solution.size();
         const unsigned int n_slots = 2 * n_pairs; // stage slots incl. the empty one of an odd q
@@ -708,7 +768,7 @@ namespace spirk_host
         gather_slots(all, g, n_slots);
         mix_slots(system_rhs, all, [&](unsigned int i, unsigned int j) { return A_inv(i, j); }, n_slots);
 
-        const double t_solver = now_ns(solution);
+        const double t_solver = now_ns(solution, true);
         this->time_rhs += t_solver - t_total;
 
         // ---- PreconditionComplex::vmult (main.cc:2129-2226, 2685-2786)
@@ -779,7 +839,7 @@ namespace spirk_host
             }
           SPIRK_CHECK(spirk_mix(dev.ctx(), 2 * mp, n_slots, system_solution.data(), N, all.data(), N, N, W.data(), 0, 0.0));
         }
-        const double t_update = now_ns(solution);
+        const double t_update = now_ns(solution, true);
         this->time_outer_solver += t_update - t_solver;
 
         // iteration bookkeeping / printed line (main.cc:2045-2064, 2540-2559)
@@ -820,7 +880,7 @@ namespace spirk_host
           SPIRK_CHECK(spirk_mix(dev.ctx(), 1, 2 * mp, solution.data(), N, system_solution.data(), N, N, w.data(), 1, 0.0));
           row.all_reduce_sum(solution);
         }
-        const double t_end = now_ns(solution);
+        const double t_end = now_ns(solution, true);
         this->time_solution_update += t_end - t_update;
         this->time_total += t_end - t_total;
         if (timestep_number == 1)

@@ -111,6 +111,11 @@ long long spirk_level_n_dofs(const spirk_level *lvl);
 /* dst = A src */
 int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst,
                    const double *src, long long stride);
+/* dst_b = laplace[b] K v_b + mass[b] M w_b in one pass over the cells (v, w: block vectors with the same stride; Dirichlet
+ * rows: dst_b = v_b).  The stage-parallel system matrix dst_s = tau K v_s + sum_j A_inv[s][j] M v_j (main.cc:1580-1592)
+ * is this with w = (A_inv (x) I) v, because M commutes with the stage mixing: one cell pass instead of two. */
+int spirk_op_apply_km(spirk_ctx *ctx, const spirk_level *lvl, int nb, double *dst, const double *v, const double *w,
+                      long long stride, const double *laplace, const double *mass);
 /* dst = rhs - A src  (Multigrid::level_v_step residual, MGSmootherPrecondition::smooth) */
 int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst,
                       const double *rhs, const double *src, long long stride);

@@ -523,6 +523,32 @@ int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *o
   return SPIRK_OK;
 }
 
+int spirk_op_apply_km(spirk_ctx *ctx, const spirk_level *lvl, int nb, double *dst, const double *v, const double *w, long long stride,
+                      const double *laplace, const double *mass)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo geo(lvl);
+  spirk_opdesc dk, dm;
+  std::memset(&dk, 0, sizeof(dk)), std::memset(&dm, 0, sizeof(dm));
+  dk.kind = dm.kind = SPIRK_OP_REAL, dk.nb = dm.nb = nb;
+  for (int b = 0; b < nb; ++b)
+    dk.laplace[b] = laplace[b], dm.mass[b] = mass[b];
+  if (int e = spirk_op_apply(ctx, lvl, &dk, dst, v, stride))
+    return e;
+  std::vector<double> tmp((size_t)stride * nb);
+  if (int e = spirk_op_apply(ctx, lvl, &dm, tmp.data(), w, stride))
+    return e;
+  for (int b = 0; b < nb; ++b)
+    for (long long i = 0; i < geo.N; ++i)
+      {
+        const int ix = i % geo.n1, iy = (i / geo.n1) % geo.n1, iz = (geo.dim == 3) ? i / ((long long)geo.n1 * geo.n1) : 1;
+        if (!geo.on_boundary(ix, iy, geo.dim == 3 ? iz : 1))
+          dst[b * stride + i] += tmp[b * stride + i];
+      }
+  return SPIRK_OK;
+}
+
 int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst, const double *rhs,
                       const double *src, long long stride)
 {

@@ -81,6 +81,29 @@ def check_op_apply(dev, dim, k, r, desc, tol=RTOL, opts=None):
     return e
 
 
+def check_apply_km(dev, dim, k, r, nb=2, opts=None):
+    """dst_b = laplace_b K v_b + mass_b M w_b in one cell pass (the stage-parallel system matrix after the A_inv mixing of
+    the source, reference main.cc:1580-1592); Dirichlet rows dst = v"""
+    lvl, olv = make_level(dim, k, r)
+    v, w = block_input(olv, nb, 21), block_input(olv, nb, 22)
+    lap = np.array([0.1, 0.2, 0.05, 0.3][:nb])
+    mass = np.array([1.0, 2.5, 0.7, 1.3][:nb])
+    vz, wz = v.copy(), w.copy()
+    vz[:, olv.bmask] = 0.0
+    wz[:, olv.bmask] = 0.0
+    ref = olv.apply(vz, 0.0, lap) + olv.apply(wz, mass, 0.0)
+    ref[:, olv.bmask] = v[:, olv.bmask]
+    with capi.Context(dev) as ctx:
+        set_options(ctx, opts)
+        dv, dw, dd = ctx.upload(v), ctx.upload(w), ctx.alloc(v.size)
+        pl, _1 = capi.darr(lap)
+        pm, _2 = capi.darr(mass)
+        ctx.call("spirk_op_apply_km", C.byref(lvl), nb, dd, dv, dw, olv.N, pl, pm)
+        out = ctx.download(dd, v.shape)
+    e = relerr(out, ref)
+    assert e < RTOL, f"op_apply_km dim={dim} k={k} r={r} nb={nb}: rel err {e}"
+
+
 def check_residual_and_cheb(dev, dim, k, r, nb=2):
     lvl, olv = make_level(dim, k, r)
     mass = np.array([16.0, 3.1618475338398158, 2.9418686642961562, 5.644106850167844][:nb])
@@ -411,6 +434,8 @@ def run_all(dev, small=True):
     check_op_apply(dev, 3, 3, 1, OP_CASES[0])
     check_residual_and_cheb(dev, 3, 4, 1)
     check_residual_and_cheb(dev, 2, 2, 3, nb=1)
+    check_apply_km(dev, 3, 4, 1)
+    check_apply_km(dev, 2, 2, 3, nb=1)
     for (dim, k, r) in [(3, 4, 1), (2, 2, 3), (3, 1, 2)]:
         check_inverse_diagonal(dev, dim, k, r)
         check_transfer(dev, dim, k, r)

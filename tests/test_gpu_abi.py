@@ -112,3 +112,15 @@ def test_v3_coupled_pair_full_size(gpu_dev, r, opts):
     """k_v3<..., APPLY, 4, NBC = 2>: complex pair and the IRK q = 2 system matrix (main.cc:1014-1028) at bench size"""
     ac.check_op_apply(gpu_dev, 3, 4, r, ac.OP_CASES[4], opts=opts)
     ac.check_op_apply(gpu_dev, 3, 4, r, ("coupled", ac.so.table("A_inv", 2).tolist(), [0.1]), opts=opts)
+
+
+@pytest.mark.parametrize("dim,k,r,nb,opts", [(3, 4, 2, 2, {}), (3, 4, 3, 1, {}), (3, 4, 4, 3, {}), (3, 4, 5, 2, {}), (3, 4, 5, 1, {"v3_schedule": 1}),
+                                             (3, 4, 6, 1, {}), (2, 2, 4, 2, {}), (3, 2, 2, 4, {}), (3, 4, 1, 2, {})])
+def test_op_apply_km(gpu_dev, dim, k, r, nb, opts):
+    """the one-pass K v + M w operator (k_v3<..., NBC = 2> with the second plane from another vector; general path elsewhere)"""
+    ac.check_apply_km(gpu_dev, dim, k, r, nb, opts)
+
+
+@pytest.mark.parametrize("dim,k,r", [(3, 4, 5), (3, 4, 6)])
+def test_transfer_full_size(gpu_dev, dim, k, r):
+    ac.check_transfer(gpu_dev, dim, k, r)
