@@ -127,7 +127,7 @@ _SIGS = {
 }
 # every symbol include/spirk_b200.h declares (tests check the library exports all of them)
 ALL_SYMBOLS = sorted(list(_SIGS) + ["spirk_backend", "spirk_last_error", "spirk_ctx_launch_count",
-                                    "spirk_level_n_dofs", "spirk_comm_xbuf_local"])
+                                    "spirk_level_n_dofs", "spirk_comm_xbuf_local", "spirk_op_fuses_own_diagonal"])
 
 
 class DeviceLib:

@@ -182,180 +182,199 @@ namespace spirk
     int       ncc;           // coarse cells along d
     long long N_out, N_in;   // entries per block
   };
-  // restriction along y or z (d = 1, 2): one thread per output entry, lanes along x (coalesced loads and stores);
-  // grid.x covers one output xy-plane, grid.y = (output z) x (vector block)
+  // Sweeps along y or z (d = 1, 2): one thread per (entry of the other two directions, coarse cell along d), lanes along
+  // x: a thread reads the 2k+1 (+2k for the coarse vertex row) fine / k+1 coarse values of its cell once and produces the
+  // cell's k coarse / 2k fine entries (index arithmetic once per cell, embedding entries as compile-time constants).
+  // grid.x covers the other two directions (flattened), grid.y = coarse cells along d, grid.z = vector blocks.
   template <int K>
   __global__ void __launch_bounds__(256) k_restrict_1d(const Sweep1D w, double *__restrict__ out, const long long os,
                                                        const double *__restrict__ in, const long long is)
   {
-    constexpr int n = K + 1;
-    __shared__ double P[(2 * K + 1) * n]; // (the row index differs from lane to lane: shared memory, not the constant bank)
-    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
-      P[t] = c_fe[K].P[t];
-    __syncthreads();
-    const unsigned pxy = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pxy >= (unsigned)(w.ex * w.ey))
+    constexpr int  n = K + 1;
+    const double  *P = c_fe[K].P;
+    const unsigned n_other = (w.d == 1) ? w.ex * w.ez : w.ex * w.ey;
+    const unsigned f       = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_other)
       return;
-    const int ox = pxy % (unsigned)w.ex, oy = pxy / (unsigned)w.ex;
-    const int oz = blockIdx.y % (unsigned)w.ez, b = blockIdx.y / (unsigned)w.ez;
-    const int i  = (w.d == 1) ? oy : oz; // coarse index along d
-    const int n1c = K * w.ncc + 1;
-    double    s  = 0.0;
-    if (i > 0 && i < n1c - 1) // coarse Dirichlet entries stay 0
+    const int ec = blockIdx.y, b = blockIdx.z;
+    // input: extent n_in along d, the output's extents elsewhere
+    long long off_in, off_out, sd_in, sd_out;
+    if (w.d == 2)
+      off_in = f, off_out = f, sd_in = sd_out = (long long)w.ex * w.ey;
+    else
       {
-        // the input has extent n_in along d and the output's extents elsewhere
-        const long long sy = w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
-        const long long sd = (w.d == 1) ? sy : sz;
-        const int       ec = i / K, il = i - ec * K;
-        const double   *p  = in + b * is + ox + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz) + (long long)(2 * K * ec) * sd;
-        if (il != 0)
-          {
-#pragma unroll
-            for (int jl = 0; jl <= 2 * K; ++jl)
-              s = fma(P[jl * n + il], p[jl * sd], s);
-          }
-        else
-          {
-            // vertex node of the coarse mesh: the fine nodes of both adjacent coarse cells (the shared one once)
-            s = p[0];
-#pragma unroll
-            for (int jl = 1; jl <= 2 * K; ++jl)
-              s = fma(P[jl * n + 0], p[jl * sd], s);
-#pragma unroll
-            for (int jl = 0; jl < 2 * K; ++jl)
-              s = fma(P[jl * n + K], p[(jl - 2 * K) * sd], s);
-          }
+        const unsigned ox = f % (unsigned)w.ex, oz = f / (unsigned)w.ex;
+        off_in = ox + (long long)w.ex * w.n_in * oz, off_out = ox + (long long)w.ex * w.ey * oz, sd_in = sd_out = w.ex;
       }
-    out[b * os + ox + (long long)w.ex * (oy + (long long)w.ey * oz)] = s;
-  }
-  // restriction along x: a block stages RPB fine rows in shared memory (coalesced), every thread contracts from there
-  template <int K, int RPB>
-  __global__ void __launch_bounds__(256) k_restrict_x(const int n1f, const int ncc, const long long rows, const long long rows_per_block,
-                                                      double *__restrict__ out, const long long os, const double *__restrict__ in,
-                                                      const long long is)
-  {
-    constexpr int n = K + 1;
-    extern __shared__ double srow[]; // RPB rows of n1f entries, then P
-    double       *P   = srow + (size_t)RPB * n1f;
-    const int     n1c = K * ncc + 1;
-    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
-      P[t] = c_fe[K].P[t];
-    __shared__ long long off_in[RPB], off_out[RPB]; // row offsets (64-bit divisions once per row, not per entry)
-    for (long long r0 = (long long)blockIdx.x * RPB; r0 < rows; r0 += (long long)gridDim.x * RPB)
+    const double *p = in + b * is + off_in + (long long)(2 * K * ec) * sd_in;
+    double       *q = out + b * os + off_out + (long long)(K * ec) * sd_out;
+    double        v[2 * K + 1];
+#pragma unroll
+    for (int jl = 0; jl <= 2 * K; ++jl)
+      v[jl] = p[jl * sd_in];
+#pragma unroll
+    for (int il = 1; il < K; ++il)
       {
-        __syncthreads();
-        const int nr = (int)min((long long)RPB, rows - r0);
-        if (threadIdx.x < nr)
-          {
-            const long long R = r0 + threadIdx.x, b = R / rows_per_block, rl = R - b * rows_per_block;
-            off_in[threadIdx.x] = b * is + rl * n1f, off_out[threadIdx.x] = b * os + rl * n1c;
-          }
-        __syncthreads();
-        for (int t = threadIdx.x; t < nr * n1f; t += blockDim.x)
-          {
-            const int rr = t / n1f, x = t - rr * n1f;
-            srow[t]      = in[off_in[rr] + x];
-          }
-        __syncthreads();
-        for (int t = threadIdx.x; t < nr * n1c; t += blockDim.x)
-          {
-            const int rr = t / n1c, i = t - rr * n1c;
-            double    s  = 0.0;
-            if (i > 0 && i < n1c - 1)
-              {
-                const int     ec = i / K, il = i - ec * K;
-                const double *p  = srow + rr * n1f + 2 * K * ec;
-                if (il != 0)
-                  {
+        double s = 0.0;
 #pragma unroll
-                    for (int jl = 0; jl <= 2 * K; ++jl)
-                      s = fma(P[jl * n + il], p[jl], s);
-                  }
-                else
-                  {
-                    s = p[0];
-#pragma unroll
-                    for (int jl = 1; jl <= 2 * K; ++jl)
-                      s = fma(P[jl * n + 0], p[jl], s);
-#pragma unroll
-                    for (int jl = 0; jl < 2 * K; ++jl)
-                      s = fma(P[jl * n + K], p[jl - 2 * K], s);
-                  }
-              }
-            out[off_out[rr] + i] = s;
-          }
+        for (int jl = 0; jl <= 2 * K; ++jl)
+          s = fma(P[jl * n + il], v[jl], s);
+        q[il * sd_out] = s;
       }
+    // the coarse vertex row at the bottom of the cell: the fine nodes of both adjacent coarse cells (the shared one once);
+    // coarse Dirichlet entries are 0
+    double s = 0.0;
+    if (ec > 0)
+      {
+        s = v[0];
+#pragma unroll
+        for (int jl = 1; jl <= 2 * K; ++jl)
+          s = fma(P[jl * n + 0], v[jl], s);
+#pragma unroll
+        for (int jl = 0; jl < 2 * K; ++jl)
+          s = fma(P[jl * n + K], p[(jl - 2 * K) * sd_in], s);
+      }
+    q[0] = s;
+    if (ec == w.ncc - 1)
+      q[K * sd_out] = 0.0;
   }
-  // prolongation along y or z: one thread per output entry, lanes along x
   template <int K>
   __global__ void __launch_bounds__(256) k_prolongate_1d(const Sweep1D w, double *__restrict__ out, const long long os,
                                                          const double *__restrict__ in, const long long is)
   {
-    constexpr int n = K + 1;
-    __shared__ double P[(2 * K + 1) * n];
-    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
-      P[t] = c_fe[K].P[t];
-    __syncthreads();
-    const unsigned pxy = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pxy >= (unsigned)(w.ex * w.ey))
+    constexpr int  n = K + 1;
+    const double  *P = c_fe[K].P;
+    const unsigned n_other = (w.d == 1) ? w.ex * w.ez : w.ex * w.ey;
+    const unsigned f       = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_other)
       return;
-    const int       ox = pxy % (unsigned)w.ex, oy = pxy / (unsigned)w.ex;
-    const int       oz = blockIdx.y % (unsigned)w.ez, b = blockIdx.y / (unsigned)w.ez;
-    const int       j  = (w.d == 1) ? oy : oz; // fine index along d
-    const long long sy = w.ex, sz = sy * ((w.d == 1) ? w.n_in : w.ey);
-    const long long sd = (w.d == 1) ? sy : sz;
-    const int       ec = min(j / (2 * K), w.ncc - 1), jl = j - 2 * K * ec;
-    const int       n1c = K * w.ncc + 1;
-    const double   *p  = in + b * is + ox + ((w.d == 1) ? 0 : oy * sy) + ((w.d == 2) ? 0 : oz * sz) + (long long)(K * ec) * sd;
-    double          s  = 0.0;
+    const int ec = blockIdx.y, b = blockIdx.z;
+    long long off_in, off_out, sd_in, sd_out;
+    if (w.d == 2)
+      off_in = f, off_out = f, sd_in = sd_out = (long long)w.ex * w.ey;
+    else
+      {
+        const unsigned ox = f % (unsigned)w.ex, oz = f / (unsigned)w.ex;
+        off_in = ox + (long long)w.ex * w.n_in * oz, off_out = ox + (long long)w.ex * w.ey * oz, sd_in = sd_out = w.ex;
+      }
+    const double *p = in + b * is + off_in + (long long)(K * ec) * sd_in;
+    double       *q = out + b * os + off_out + (long long)(2 * K * ec) * sd_out;
+    double        c[n];
 #pragma unroll
     for (int il = 0; il <= K; ++il)
+      c[il] = p[il * sd_in];
+    if (ec == 0) // coarse Dirichlet entries are read as 0
+      c[0] = 0.0;
+    if (ec == w.ncc - 1)
+      c[K] = 0.0;
+#pragma unroll
+    for (int jl = 0; jl < 2 * K; ++jl)
       {
-        const int i = K * ec + il;
-        if (i > 0 && i < n1c - 1) // coarse Dirichlet entries are read as 0
-          s = fma(P[jl * n + il], p[il * sd], s);
+        double s = 0.0;
+#pragma unroll
+        for (int il = 0; il <= K; ++il)
+          s = fma(P[jl * n + il], c[il], s);
+        q[jl * sd_out] = s;
       }
-    out[b * os + ox + (long long)w.ex * (oy + (long long)w.ey * oz)] = s;
+    if (ec == w.ncc - 1)
+      q[2 * K * sd_out] = c[K]; // the top fine plane coincides with the (Dirichlet) coarse one
   }
-  // prolongation along x, added into the fine vector: RPB coarse rows staged in shared memory per block
+  // restriction along x: a block stages RPB fine rows in shared memory (coalesced), thread (lane, row) contracts the
+  // cells lane, lane + 32, ... of its row into a staged coarse row, which is stored coalesced
   template <int K, int RPB>
-  __global__ void __launch_bounds__(256) k_prolongate_x_add(const int n1f, const int ncc, const long long rows, const long long rows_per_block,
-                                                            double *__restrict__ out, const long long os, const double *__restrict__ in,
-                                                            const long long is)
+  __global__ void __launch_bounds__(32 * RPB) k_restrict_x(const int n1f, const int ncc, const long long rows, const long long rows_per_block,
+                                                           double *__restrict__ out, const long long os, const double *__restrict__ in,
+                                                           const long long is)
   {
     constexpr int n = K + 1;
-    extern __shared__ double srow[]; // RPB rows of n1c entries, then P
+    extern __shared__ double srow[]; // RPB fine rows of n1f entries, RPB coarse rows of n1c entries
+    const double *P   = c_fe[K].P;
     const int     n1c = K * ncc + 1;
-    double       *P   = srow + (size_t)RPB * n1c;
-    for (int t = threadIdx.x; t < (2 * K + 1) * n; t += blockDim.x)
-      P[t] = c_fe[K].P[t];
-    __shared__ long long off_in[RPB], off_out[RPB];
+    double       *fr  = srow + threadIdx.y * n1f, *cr = srow + RPB * n1f + threadIdx.y * n1c;
     for (long long r0 = (long long)blockIdx.x * RPB; r0 < rows; r0 += (long long)gridDim.x * RPB)
       {
-        __syncthreads();
-        const int nr = (int)min((long long)RPB, rows - r0);
-        if (threadIdx.x < nr)
+        const long long R = r0 + threadIdx.y;
+        const bool      live = R < rows;
+        const long long b = live ? R / rows_per_block : 0, rl = R - b * rows_per_block;
+        __syncwarp(); // (every warp owns one fine and one coarse row of the staging area: no block-wide barrier)
+        if (live)
+          for (int x = threadIdx.x; x < n1f; x += 32)
+            fr[x] = in[b * is + rl * n1f + x];
+        __syncwarp();
+        if (live)
           {
-            const long long R = r0 + threadIdx.x, b = R / rows_per_block, rl = R - b * rows_per_block;
-            off_in[threadIdx.x] = b * is + rl * n1c, off_out[threadIdx.x] = b * os + rl * n1f;
+            for (int ec = threadIdx.x; ec < ncc; ec += 32)
+              {
+                const double *p = fr + 2 * K * ec;
+                double        v[2 * K + 1];
+#pragma unroll
+                for (int jl = 0; jl <= 2 * K; ++jl)
+                  v[jl] = p[jl];
+#pragma unroll
+                for (int il = 1; il < K; ++il)
+                  {
+                    double s = 0.0;
+#pragma unroll
+                    for (int jl = 0; jl <= 2 * K; ++jl)
+                      s = fma(P[jl * n + il], v[jl], s);
+                    cr[K * ec + il] = s;
+                  }
+                double s = 0.0;
+                if (ec > 0)
+                  {
+                    s = v[0];
+#pragma unroll
+                    for (int jl = 1; jl <= 2 * K; ++jl)
+                      s = fma(P[jl * n + 0], v[jl], s);
+#pragma unroll
+                    for (int jl = 0; jl < 2 * K; ++jl)
+                      s = fma(P[jl * n + K], p[jl - 2 * K], s);
+                  }
+                cr[K * ec] = s;
+              }
+            if (threadIdx.x == 0)
+              cr[n1c - 1] = 0.0;
           }
-        __syncthreads();
-        for (int t = threadIdx.x; t < nr * n1c; t += blockDim.x)
+        __syncwarp();
+        if (live)
+          for (int i = threadIdx.x; i < n1c; i += 32)
+            out[b * os + rl * n1c + i] = cr[i];
+      }
+  }
+  // prolongation along x, added into the fine vector: warp `row` stages its coarse row in shared memory
+  template <int K, int RPB>
+  __global__ void __launch_bounds__(32 * RPB) k_prolongate_x_add(const int n1f, const int ncc, const long long rows,
+                                                                 const long long rows_per_block, double *__restrict__ out, const long long os,
+                                                                 const double *__restrict__ in, const long long is)
+  {
+    constexpr int n = K + 1;
+    extern __shared__ double srow[]; // RPB coarse rows of n1c entries, then P
+    const int     n1c = K * ncc + 1;
+    double       *P   = srow + (size_t)RPB * n1c;
+    double       *cr  = srow + threadIdx.y * n1c;
+    for (int t = threadIdx.y * 32 + threadIdx.x; t < (2 * K + 1) * n; t += 32 * RPB)
+      P[t] = c_fe[K].P[t];
+    __syncthreads();
+    for (long long r0 = (long long)blockIdx.x * RPB; r0 < rows; r0 += (long long)gridDim.x * RPB)
+      {
+        const long long R = r0 + threadIdx.y;
+        if (R >= rows)
+          continue; // (no block-wide barrier below: the rows of a block are independent warps)
+        const long long b = R / rows_per_block, rl = R - b * rows_per_block;
+        __syncwarp();
+        for (int i = threadIdx.x; i < n1c; i += 32)
+          cr[i] = (i > 0 && i < n1c - 1) ? in[b * is + rl * n1c + i] : 0.0; // Dirichlet: 0
+        __syncwarp();
+        double *o = out + b * os + rl * n1f;
+        for (int j = threadIdx.x; j < n1f; j += 32)
           {
-            const int rr = t / n1c, i = t - rr * n1c;
-            srow[t]      = (i > 0 && i < n1c - 1) ? in[off_in[rr] + i] : 0.0; // Dirichlet: 0
-          }
-        __syncthreads();
-        for (int t = threadIdx.x; t < nr * n1f; t += blockDim.x)
-          {
-            const int     rr = t / n1f, j = t - rr * n1f;
             const int     ec = min(j / (2 * K), ncc - 1), jl = j - 2 * K * ec;
-            const double *p  = srow + rr * n1c + K * ec;
+            const double *p  = cr + K * ec;
             double        s  = 0.0;
 #pragma unroll
             for (int il = 0; il <= K; ++il)
               s = fma(P[jl * n + il], p[il], s);
-            out[off_out[rr] + j] += s;
+            o[j] += s;
           }
       }
   }

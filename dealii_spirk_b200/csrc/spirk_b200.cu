@@ -490,6 +490,19 @@ static int fast_apply(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, V2Mo
     }
   return v2_apply(ctx, g, op, mode, dst, src, x_old, rhs, dinv, stride, f1, f2);
 }
+// dst = A src into a scratch vector whose blocks sit at stride N: the fastest kernel that covers the operator
+static int apply_fast_or_any(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, double *dst, const double *src, long long src_stride,
+                             long long dst_stride)
+{
+  if (src_stride == dst_stride)
+    {
+      int st = fast_apply(ctx, g, op, V2_APPLY, dst, src, nullptr, nullptr, nullptr, src_stride, nullptr, nullptr);
+      if (st != SPIRK_ERR_UNSUPPORTED)
+        return st;
+    }
+  return apply_any(ctx, g, op, dst, src, dst_stride);
+}
+
 int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *dst, const double *src,
                    long long stride)
 {
@@ -556,7 +569,9 @@ int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc
   }
   if (int e = ensure_scratch(ctx, (size_t)g.N * op->nb))
     return e;
-  if (int e = apply_any(ctx, g, op, ctx->d_scratch, src, g.N))
+  // unfused: A src through the fastest kernel that covers the operator (coupled pairs: the plane-streaming apply), then
+  // the pointwise epilogue
+  if (int e = apply_fast_or_any(ctx, g, op, ctx->d_scratch, src, stride, g.N))
     return e;
   k_residual_epilogue<<<grid_for(ctx, g.N * op->nb, 256), 256, 0, ctx->stream>>>(g.N, op->nb, dst, rhs, ctx->d_scratch, stride, g.N);
   SPIRK_LAUNCH_CHECK(ctx);
@@ -593,7 +608,7 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
         if (int e = spirk_op_inverse_diagonal(ctx, lvl, d + (size_t)b * g.N, op->mass[b], op->laplace[b]))
           return e;
     }
-  if (int e = apply_any(ctx, g, op, ctx->d_scratch, x, g.N))
+  if (int e = apply_fast_or_any(ctx, g, op, ctx->d_scratch, x, stride, g.N))
     return e;
   ChebFactors f;
   for (int b = 0; b < op->nb; ++b)
@@ -603,6 +618,14 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
     own_dinv ? g.N : stride);
   SPIRK_LAUNCH_CHECK(ctx);
   return SPIRK_OK;
+}
+
+int spirk_op_fuses_own_diagonal(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op)
+{
+  if (!lvl || !op || op->kind != SPIRK_OP_REAL || ctx->opt_apply_variant != 0)
+    return 0;
+  const Geo g = make_geo(lvl);
+  return (g.dim == 3 && g.k == 4 && g.nc % 4 == 0 && g.nc >= 8) ? 1 : 0; // the shapes v3_apply covers
 }
 
 int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
@@ -716,7 +739,10 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
     }
   // expand z, then y (one thread per entry, lanes along x), then x from rows staged in shared memory, adding into the fine vector
   constexpr int RPB = 8;
-  const auto grid_1d = [&](const Sweep1D &w) { return dim3((unsigned)((w.ex * w.ey + 255) / 256), (unsigned)(w.ez * nb)); };
+  const auto grid_1d = [&](const Sweep1D &w) {
+    return dim3((unsigned)(((w.d == 1 ? w.ex * w.ez : w.ex * w.ey) + 255) / 256), (unsigned)ncc, (unsigned)nb);
+  };
+  const dim3      blk_x(32, RPB);
   const size_t    smem_x = sizeof(double) * ((size_t)RPB * ncn + (2 * g.k + 1) * (g.k + 1));
   if (g.dim == 3)
     {
@@ -729,7 +755,7 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
       SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, t2, wz.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
       const long long rpb = (long long)nf * nf, rows = rpb * nb;
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, fine, fs, t1, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
@@ -742,7 +768,7 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
       SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, coarse, cs)));
       SPIRK_LAUNCH_CHECK(ctx);
       const long long rpb = nf, rows = rpb * nb;
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, fine, fs, t1, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
@@ -782,8 +808,11 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
   // contract x (fine rows staged in shared memory), then y, then z (one thread per entry, lanes along x): every coarse
   // entry is written exactly once
   constexpr int RPB = 8;
-  const auto grid_1d = [&](const Sweep1D &w) { return dim3((unsigned)((w.ex * w.ey + 255) / 256), (unsigned)(w.ez * nb)); };
-  const size_t    smem_x = sizeof(double) * ((size_t)RPB * nf + (2 * g.k + 1) * (g.k + 1));
+  const auto grid_1d = [&](const Sweep1D &w) {
+    return dim3((unsigned)(((w.d == 1 ? w.ex * w.ez : w.ex * w.ey) + 255) / 256), (unsigned)ncc, (unsigned)nb);
+  };
+  const dim3      blk_x(32, RPB);
+  const size_t    smem_x = sizeof(double) * ((size_t)RPB * (nf + ncn));
   if (g.dim == 3)
     {
       const Sweep1D wx = make_sweep(0, ncn, nf, nf, nf, ncc), wy = make_sweep(1, ncn, ncn, nf, nf, ncc), wz = make_sweep(2, ncn, ncn, ncn, nf, ncc);
@@ -791,7 +820,7 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
         return e;
       double         *t1 = ctx->d_scratch, *t2 = ctx->d_scratch + (size_t)nb * wx.N_out;
       const long long rpb = (long long)nf * nf, rows = rpb * nb;
-      SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+      SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, t1, wx.N_out, fine, fs)));
       SPIRK_LAUNCH_CHECK(ctx);
       SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t2, wy.N_out, t1, wx.N_out)));
@@ -806,7 +835,7 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
         return e;
       double         *t1 = ctx->d_scratch;
       const long long rpb = nf, rows = rpb * nb;
-      SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), 256, smem_x, ctx->stream>>>(
+      SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, t1, wx.N_out, fine, fs)));
       SPIRK_LAUNCH_CHECK(ctx);
       SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, coarse, cs, t1, wx.N_out)));

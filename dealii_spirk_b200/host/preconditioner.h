@@ -184,7 +184,9 @@ namespace spirk_host
         for (int i = 0; i < nb; ++i)
           f[i] = 1.0 / L.theta[i];
         const spirk_opdesc op = opdesc(l);
-        bool own_dinv = op.kind == SPIRK_OP_REAL && (int)L.dinv_mass.size() == nb;
+        // the kernel forms D^-1 on the fly only where that is fused into the cell pass (elsewhere it would be recomputed
+        // into scratch memory on every call: pass the stored diagonal)
+        bool own_dinv = op.kind == SPIRK_OP_REAL && (int)L.dinv_mass.size() == nb && spirk_op_fuses_own_diagonal(dev->ctx(), &L.level, &op);
         for (int i = 0; own_dinv && i < nb; ++i)
           own_dinv = L.dinv_mass[i] == op.mass[i] && L.dinv_laplace[i] == op.laplace[i];
         std::vector<double> rhok(nb), sigma(nb);

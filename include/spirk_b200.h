@@ -126,6 +126,9 @@ int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc
 int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op,
                        double *x_new, const double *x, const double *x_old, const double *rhs,
                        const double *dinv, long long stride, const double *f1, const double *f2);
+/* 1 if spirk_op_cheb_step / spirk_op_cheb_first with dinv == NULL run on a fused kernel that forms the inverse diagonal on
+ * the fly for this level and operator; 0 if they would materialise it on every call (pass the stored vector then) */
+int spirk_op_fuses_own_diagonal(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op);
 /* the first two Chebyshev iterates from a zero start in one pass over rhs (PreconditionChebyshev::vmult, iteration 0
  * and 1): x1 = f0[b] dinv .* rhs;  x2 = x1 + f1[b] x1 + f2[b] dinv .* (rhs - A x1), dinv = the inverse diagonal of op
  * itself (REAL operators).  24 B per DoF instead of 48 for spirk_vec_scale_pointwise + spirk_op_cheb_step. */

@@ -523,6 +523,8 @@ int spirk_op_apply(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *o
   return SPIRK_OK;
 }
 
+int spirk_op_fuses_own_diagonal(spirk_ctx *, const spirk_level *, const spirk_opdesc *) { return 0; }
+
 int spirk_op_apply_km(spirk_ctx *ctx, const spirk_level *lvl, int nb, double *dst, const double *v, const double *w, long long stride,
                       const double *laplace, const double *mass)
 {
