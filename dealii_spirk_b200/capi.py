@@ -15,7 +15,7 @@ dp = C.POINTER(C.c_double)
 
 
 class Level(C.Structure):
-    _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("n_cells_1d", C.c_int), ("reserved", C.c_int)]
+    _fields_ = [("dim", C.c_int), ("degree", C.c_int), ("n_cells_1d", C.c_int), ("slab", C.c_int)]
 
     @property
     def n1(self):
@@ -101,6 +101,15 @@ _SIGS = {
     "spirk_vec_dot": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, dp],
     "spirk_vec_add_and_dot": [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_longlong, dp],
     "spirk_vec_sum": [C.c_void_p, C.c_void_p, C.c_longlong, dp],
+    "spirk_vec_dot_strided": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, dp],
+    "spirk_vec_sum_strided": [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, dp],
+    "spirk_vec_add_and_dot_strided": [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                      C.c_longlong, dp],
+    "spirk_gmres_mgs_strided": [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_int, C.c_longlong, dp, dp],
+    "spirk_problem_error_norms_partial": [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_double, dp, dp],
+    "spirk_comm_split": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)],
+    "spirk_comm_allreduce_max": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong],
+    "spirk_halo_exchange": [C.c_void_p, C.c_void_p, C.POINTER(Level), C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int],
     "spirk_gmres_mgs": [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_longlong, dp, dp],
     "spirk_mix": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong,
                   dp, C.c_int, C.c_double],

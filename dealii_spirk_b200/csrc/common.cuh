@@ -24,21 +24,35 @@ namespace spirk
     double Mv, Kv; // assembled 1-D diagonals at a vertex node shared by two cells: Mh[k][k] + Mh[0][0]
   };
 
-  // geometry handed to kernels by value
+  // geometry handed to kernels by value.  A level may be a z-SLAB of the mesh (3-D; spirk_level::slab): cell layers
+  // [L_lo, L_hi) of the nc, owned node planes [zo0, zo1) (a vertex plane between two slabs belongs to the upper one, the top
+  // plane of the domain to the last slab).  Vectors of a slab level hold their owned planes contiguously; pointers handed
+  // to the library point at the first OWNED entry, and SPIRK_SLAB_PAD_LO planes below / SPIRK_SLAB_PAD_HI planes above it
+  // are ghost planes (filled by spirk_halo_exchange).  N = owned entries.  Unpartitioned: L = [0, nc), zo = [0, n1).
   struct Geo
   {
     int       dim, k, n, nc, n1;
     long long N;
     double    h;
+    int       col_rank, col_size, coarse_replicated;
+    int       L_lo, L_hi, zo0, zo1, gh_lo, gh_hi;
+    long long plane;
   };
 
   inline Geo make_geo(const spirk_level *l)
   {
     Geo g;
     g.dim = l->dim, g.k = l->degree, g.n = l->degree + 1, g.nc = l->n_cells_1d;
-    g.n1 = g.k * g.nc + 1;
-    g.N  = (long long)g.n1 * g.n1 * (g.dim == 3 ? g.n1 : 1);
-    g.h  = 1.0 / g.nc;
+    g.n1    = g.k * g.nc + 1;
+    g.plane = (g.dim == 3) ? (long long)g.n1 * g.n1 : g.n1;
+    g.h     = 1.0 / g.nc;
+    g.col_size = (l->slab >> 8) & 0xff, g.col_rank = l->slab & 0xff, g.coarse_replicated = (l->slab >> 16) & 1;
+    if (g.col_size <= 1)
+      g.col_size = 1, g.col_rank = 0;
+    g.L_lo = (int)((long long)g.nc * g.col_rank / g.col_size), g.L_hi = (int)((long long)g.nc * (g.col_rank + 1) / g.col_size);
+    g.zo0 = g.k * g.L_lo, g.zo1 = (g.L_hi == g.nc) ? g.n1 : g.k * g.L_hi;
+    g.gh_lo = (g.col_size > 1) ? SPIRK_SLAB_PAD_LO(g.k) : 0, g.gh_hi = (g.col_size > 1) ? SPIRK_SLAB_PAD_HI : 0;
+    g.N     = (g.dim == 3) ? g.plane * (g.zo1 - g.zo0) : (long long)g.n1 * g.n1;
     return g;
   }
 

@@ -179,8 +179,11 @@ namespace spirk
   {
     int       d, ex, ey, ez; // direction, output extents
     int       n_in;          // input extent along d
-    int       ncc;           // coarse cells along d
+    int       ncc;           // coarse cells along d (of the whole mesh)
     long long N_out, N_in;   // entries per block
+    // z-slabs (d = 2 only): first coarse cell handled (grid.y counts the local ones) and the global index of local plane
+    // 0 of the input / output array
+    int ec0, in_z0, out_z0;
   };
   // Sweeps along y or z (d = 1, 2): one thread per (entry of the other two directions, coarse cell along d), lanes along
   // x: a thread reads the 2k+1 (+2k for the coarse vertex row) fine / k+1 coarse values of its cell once and produces the
@@ -196,7 +199,7 @@ namespace spirk
     const unsigned f       = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_other)
       return;
-    const int ec = blockIdx.y, b = blockIdx.z;
+    const int ec = blockIdx.y + w.ec0, b = blockIdx.z;
     // input: extent n_in along d, the output's extents elsewhere
     long long off_in, off_out, sd_in, sd_out;
     if (w.d == 2)
@@ -206,8 +209,8 @@ namespace spirk
         const unsigned ox = f % (unsigned)w.ex, oz = f / (unsigned)w.ex;
         off_in = ox + (long long)w.ex * w.n_in * oz, off_out = ox + (long long)w.ex * w.ey * oz, sd_in = sd_out = w.ex;
       }
-    const double *p = in + b * is + off_in + (long long)(2 * K * ec) * sd_in;
-    double       *q = out + b * os + off_out + (long long)(K * ec) * sd_out;
+    const double *p = in + b * is + off_in + (long long)(2 * K * ec - w.in_z0) * sd_in;
+    double       *q = out + b * os + off_out + (long long)(K * ec - w.out_z0) * sd_out;
     double        v[2 * K + 1];
 #pragma unroll
     for (int jl = 0; jl <= 2 * K; ++jl)
@@ -248,7 +251,7 @@ namespace spirk
     const unsigned f       = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_other)
       return;
-    const int ec = blockIdx.y, b = blockIdx.z;
+    const int ec = blockIdx.y + w.ec0, b = blockIdx.z;
     long long off_in, off_out, sd_in, sd_out;
     if (w.d == 2)
       off_in = f, off_out = f, sd_in = sd_out = (long long)w.ex * w.ey;
@@ -257,8 +260,8 @@ namespace spirk
         const unsigned ox = f % (unsigned)w.ex, oz = f / (unsigned)w.ex;
         off_in = ox + (long long)w.ex * w.n_in * oz, off_out = ox + (long long)w.ex * w.ey * oz, sd_in = sd_out = w.ex;
       }
-    const double *p = in + b * is + off_in + (long long)(K * ec) * sd_in;
-    double       *q = out + b * os + off_out + (long long)(2 * K * ec) * sd_out;
+    const double *p = in + b * is + off_in + (long long)(K * ec - w.in_z0) * sd_in;
+    double       *q = out + b * os + off_out + (long long)(2 * K * ec - w.out_z0) * sd_out;
     double        c[n];
 #pragma unroll
     for (int il = 0; il <= K; ++il)
@@ -503,6 +506,40 @@ namespace spirk
     }
     block_reduce_store<RT>(s, partials + blockIdx.x);
   }
+  // the reductions over a block vector whose blocks sit at a stride larger than their length (z-slab vectors carry ghost
+  // planes between the blocks): blockIdx.y = block, partial sums in partials[blockIdx.y * gridDim.x + blockIdx.x]
+  __global__ void __launch_bounds__(RT) k_dot_strided(const double *__restrict__ x, const double *__restrict__ y, const long long n,
+                                                      const long long stride, double *partials)
+  {
+    const double *xb = x + blockIdx.y * stride, *yb = y + blockIdx.y * stride;
+    double        s  = 0.0;
+    SPIRK_GRID_STRIDE(i, n) s = fma(xb[i], yb[i], s);
+    block_reduce_store<RT>(s, partials + blockIdx.y * gridDim.x + blockIdx.x);
+  }
+  __global__ void __launch_bounds__(RT) k_sum_strided(const double *__restrict__ x, const long long n, const long long stride, double *partials)
+  {
+    const double *xb = x + blockIdx.y * stride;
+    double        s  = 0.0;
+    SPIRK_GRID_STRIDE(i, n) s += xb[i];
+    block_reduce_store<RT>(s, partials + blockIdx.y * gridDim.x + blockIdx.x);
+  }
+  // v += a V (a from the host, or -(*coef) from device memory); partial of v . W (W may alias v)
+  __global__ void __launch_bounds__(RT) k_add_and_dot_strided(double *v, const double a_host, const double *__restrict__ coef,
+                                                              const double *__restrict__ V, const double *W, const long long n,
+                                                              const long long stride, double *partials)
+  {
+    const double    a = coef ? -(*coef) : a_host;
+    const long long o = blockIdx.y * stride;
+    double          s = 0.0;
+    SPIRK_GRID_STRIDE(i, n)
+    {
+      const double t = fma(a, V[o + i], v[o + i]);
+      const double w = (W == v) ? t : W[o + i];
+      v[o + i]       = t;
+      s              = fma(t, w, s);
+    }
+    block_reduce_store<RT>(s, partials + blockIdx.y * gridDim.x + blockIdx.x);
+  }
   // result[slot] = sum of partials[0..nblocks)   (fixed order: deterministic)
   __global__ void __launch_bounds__(RT) k_finish(const double *__restrict__ partials, const int nblocks, double *result)
   {
@@ -622,7 +659,7 @@ namespace spirk
   {
     SPIRK_GRID_STRIDE(i, g.N)
     {
-      const int  ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? i / ((long long)g.n1 * g.n1) : 1;
+      const int  ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? (int)(i / ((long long)g.n1 * g.n1)) + g.zo0 : 1;
       const bool bd = on_bdry(ix, g.n1) || on_bdry(iy, g.n1) || (g.dim == 3 && on_bdry(iz, g.n1));
       double     v  = t1[ix] * t1[iy] * scale;
       if (g.dim == 3)
@@ -638,7 +675,7 @@ namespace spirk
     {
       const int       b  = e / g.N;
       const long long i  = e - b * g.N;
-      const int       ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? i / ((long long)g.n1 * g.n1) : 1;
+      const int       ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? (int)(i / ((long long)g.n1 * g.n1)) + g.zo0 : 1;
       if (!(on_bdry(ix, g.n1) || on_bdry(iy, g.n1) || (g.dim == 3 && on_bdry(iz, g.n1))))
         y[b * ys + i] += x[b * xs + i];
     }
@@ -650,7 +687,7 @@ namespace spirk
     {
       const int       b  = e / g.N;
       const long long i  = e - b * g.N;
-      const int       ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? i / ((long long)g.n1 * g.n1) : 1;
+      const int       ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? (int)(i / ((long long)g.n1 * g.n1)) + g.zo0 : 1;
       if (on_bdry(ix, g.n1) || on_bdry(iy, g.n1) || (g.dim == 3 && on_bdry(iz, g.n1)))
         u[b * stride + i] = 0.0;
     }
@@ -669,15 +706,16 @@ namespace spirk
     __shared__ double su[NL], s1[N1], s2[N2], red[128];
     const double *Be = c_fe[K].Be, *xe = c_fe[K].xe, *we = c_fe[K].we;
     const int     nc = g.nc, n1 = g.n1;
-    const long long ncells = (DIM == 3) ? (long long)nc * nc * nc : (long long)nc * nc;
+    // the cells of this z-slab (all cells of an unpartitioned level); u is indexed by local plane (one ghost plane above)
+    const long long ncells = (DIM == 3) ? (long long)nc * nc * (g.L_hi - g.L_lo) : (long long)nc * nc;
     double          lsum = 0.0, lmax = 0.0;
     const double    twopi = 6.283185307179586476925286766559;
     for (long long c = blockIdx.x; c < ncells; c += gridDim.x)
       {
-        const int cx = c % nc, cy = (c / nc) % nc, cz = (DIM == 3) ? c / ((long long)nc * nc) : 0;
+        const int cx = c % nc, cy = (c / nc) % nc, cz = (DIM == 3) ? (int)(c / ((long long)nc * nc)) + g.L_lo : 0;
         for (int l = threadIdx.x; l < NL; l += blockDim.x)
           {
-            const int ix = cx * K + l % n, iy = cy * K + (l / n) % n, iz = (DIM == 3) ? cz * K + l / (n * n) : 0;
+            const int ix = cx * K + l % n, iy = cy * K + (l / n) % n, iz = (DIM == 3) ? cz * K + l / (n * n) - g.zo0 : 0;
             su[l]        = u[ix + (long long)n1 * (iy + (long long)n1 * iz)];
           }
         __syncthreads();

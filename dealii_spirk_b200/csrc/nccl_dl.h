@@ -23,6 +23,7 @@ namespace spirk
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t)                  = nullptr;
     ncclResult_t (*GroupStart)()                                                                          = nullptr;
     ncclResult_t (*GroupEnd)()                                                                            = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *)                         = nullptr;
     const char *(*GetErrorString)(ncclResult_t)                                                           = nullptr;
     bool        ok = false;
     std::string error;
@@ -62,6 +63,7 @@ namespace spirk
       SPIRK_NCCL_SYM(Recv, "ncclRecv")
       SPIRK_NCCL_SYM(GroupStart, "ncclGroupStart")
       SPIRK_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+      SPIRK_NCCL_SYM(CommSplit, "ncclCommSplit")
       SPIRK_NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef SPIRK_NCCL_SYM
       api.ok = true;

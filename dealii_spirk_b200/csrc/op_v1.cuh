@@ -362,7 +362,7 @@ namespace spirk
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.N; i += (long long)gridDim.x * blockDim.x)
       {
-        const int  ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? i / ((long long)g.n1 * g.n1) : 1;
+        const int  ix = i % g.n1, iy = (i / g.n1) % g.n1, iz = (g.dim == 3) ? (int)(i / ((long long)g.n1 * g.n1)) + g.zo0 : 1;
         const bool bd = on_bdry(ix, g.n1) || on_bdry(iy, g.n1) || (g.dim == 3 && on_bdry(iz, g.n1));
         double     d  = 0.0;
         if (!bd)

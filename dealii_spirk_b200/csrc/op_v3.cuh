@@ -156,6 +156,9 @@ namespace spirk
     int          *state;  // per range boundary: 0 idle, 1 claimed by the first arrival, 2 its partial sums are published
     double       *carry;  // per range boundary: OX * OY partial sums
     long long     rows_per_block; // stride / n1: the blocks continue the row sequence of block 0
+    int           L_lo, L_hi;     // cell layers of this z-slab ([0, nc) for the whole mesh)
+    int           zo0;            // global index of the first owned node plane = local plane 0 of every vector
+    int           gh_lo;          // ghost planes below the owned range (the tensor maps start there)
     int           sh_src, sh_o0, sh_o1; // element shift of the 16-byte aligned map base below the vector
     alignas(64) CUtensorMap tm_src, tm_o0, tm_o1; // staged nodes; operand 0 (rhs | x_old); operand 1 (rhs)
   };
@@ -279,7 +282,7 @@ namespace spirk
             col            = item % ncols;
             const int rest = item / ncols, ch = rest % a.lock_nch;
             b              = rest / a.lock_nch;
-            L0 = min(nc, ch * a.lock_len), L1 = min(nc, (ch + 1) * a.lock_len);
+            L0 = min(a.L_hi, a.L_lo + ch * a.lock_len), L1 = min(a.L_hi, a.L_lo + (ch + 1) * a.lock_len);
           }
         else
           {
@@ -300,8 +303,10 @@ namespace spirk
         const double    Kv = kp[V3_NKP - 1];
         const long long boff = (long long)b * a.stride;
         const double   *src  = a.src + boff;
-        const int       zf   = (L0 > 0 && !a.dyn) ? L0 - 1 : L0; // first layer that is processed (recomputed if < L0)
-        const bool      carry_in = a.dyn && L0 > 0, carry_out = a.dyn && L1 < nc; // range boundaries shared with another CTA
+        // range boundaries shared with another CTA of this launch (at the bottom of a z-slab the layer below is recomputed
+        // from the ghost planes; the top plane of a slab belongs to the slab above)
+        const bool      carry_in = a.dyn && L0 > a.L_lo, carry_out = a.dyn && L1 < a.L_hi;
+        const int       zf   = (L0 > 0 && !carry_in) ? L0 - 1 : L0; // first layer that is processed (recomputed if < L0)
         const int       nsteps = 1 + K * (L1 - zf);        // node planes K zf .. K L1
         const bool      has_xo = (a.x_old != nullptr);
         const bool      edge_x = (tx == 0) || (tx == a.ntx - 1);
@@ -331,7 +336,7 @@ namespace spirk
         // Rows of all planes and blocks form ONE sequence of pitch n1 (row index R = y + n1 (z + n1 b)); the tensor
         // maps view pairs of rows as super-rows of pitch 2 n1 (a multiple of 16 bytes although n1 is odd), so the
         // even and the odd rows of a staged plane are one 2-D box each.
-        const long long Rb0 = (long long)b * a.rows_per_block + (long long)n1 * (K * zf) + (gy0 - K); // staged row 0 of step 0
+        const long long Rb0 = (long long)b * a.rows_per_block + (long long)n1 * (K * zf - a.zo0 + a.gh_lo) + (gy0 - K); // staged row 0 of step 0
         const bool      has_o0 = (MODE == V2_RESIDUAL) || (MODE == V2_CHEB_OWN && has_xo);
         auto            issue  = [&](const int sidx) {
           if (tid == C::ISSUER)
@@ -701,7 +706,7 @@ namespace spirk
                   // b = src of this plane: g = kappa b; the first iterate x1 = f0 D^-1 b is stored here, plane by plane
                   const double   *sd1 = SD1 + ((ZL % K) * K + i0) * K + (xl % K);
                   const int       gx = gx0 + xl, gyf = gy0 + K * ys + i0;
-                  double         *d1p = const_cast<double *>(a.dinv) + boff + gx + (long long)n1 * gyf + plane * P;
+                  double         *d1p = const_cast<double *>(a.dinv) + boff + gx + (long long)n1 * gyf + plane * (P - a.zo0);
 #pragma unroll
                   for (int i = 0; i < NPT; ++i)
                     {
@@ -757,7 +762,7 @@ namespace spirk
                   if (Lc >= L0)
                     {
                       const int       gx = gx0 + xl, gy = gy0 + K * ys + i0; // first of the NPT nodes
-                      const long long j0 = boff + gx + (long long)n1 * gy + plane * (K * Lc);
+                      const long long j0 = boff + gx + (long long)n1 * gy + plane * (K * Lc - a.zo0);
                       const bool      anyb = (gx == 0) || (gy == 0) || (Lc == 0);
                       const double   *sds  = SDS + i0 * K + (xl % K);
                       const double    sca  = (MODE == V2_APPLY) ? sc : -sc;
@@ -779,7 +784,7 @@ namespace spirk
                       // layer below, the top plane of a range that ends below the top those of the layer above: the two CTAs
                       // meet at `state`; the first one publishes its partial sums, the second one adds them and stores.
                       auto combine = [&](const int Lb, const double(&part)[NPT]) {
-                        const int bnd = (b * ncols + col) * a.lock_nch + Lb / a.lock_len;
+                        const int bnd = (b * ncols + col) * a.lock_nch + (Lb - a.L_lo) / a.lock_len;
                         double   *cb  = a.carry + (size_t)bnd * (NY * NPT);
                         if (tid == 0)
                           QS[2] = atomicCAS(a.state + bnd, 0, 1);
@@ -806,7 +811,7 @@ namespace spirk
                             asm volatile("bar.sync 1, %0;" ::"r"(NY) : "memory");
                             // the plane is stored as plane 0 of layer Lb (this CTA sees it as z = K of layer Lb - 1 or as
                             // z = 0 of layer Lb: same node class, same index)
-                            const long long jb = boff + gx + (long long)n1 * gy + plane * (K * Lb);
+                            const long long jb = boff + gx + (long long)n1 * gy + plane * (K * Lb - a.zo0);
 #pragma unroll
                             for (int i = 0; i < NPT; ++i)
                               {
@@ -873,11 +878,11 @@ namespace spirk
                 {
                   const int oye = OY + (ty == a.nty - 1 ? 1 : 0);
                   for (int e = ht; e < K * oye; e += hs)
-                    v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye), f0);
+                    v3_identity<MODE>(a, f1, f2, boff + (n1 - 1) + (long long)n1 * (gy0 + e % oye) + plane * (K * Lc + e / oye - a.zo0), f0);
                 }
               if (ty == a.nty - 1)
                 for (int e = ht; e < K * OX; e += hs)
-                  v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX), f0);
+                  v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % OX) + (long long)n1 * (n1 - 1) + plane * (K * Lc + e / OX - a.zo0), f0);
             }
           if (C::PIPE)
             {
@@ -917,7 +922,7 @@ namespace spirk
           {
             const int oxe = OX + (tx == a.ntx - 1 ? 1 : 0), oye = OY + (ty == a.nty - 1 ? 1 : 0);
             for (int e = tid; e < oxe * oye; e += NT)
-              v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % oxe) + (long long)n1 * (gy0 + e / oxe) + plane * (n1 - 1), f0);
+              v3_identity<MODE>(a, f1, f2, boff + (gx0 + e % oxe) + (long long)n1 * (gy0 + e / oxe) + plane * (n1 - 1 - a.zo0), f0);
           }
       }
     if (a.dyn && tid == 0 && atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1)
@@ -1002,19 +1007,22 @@ namespace spirk
         attr_set = smem;
       }
     const int       l2p     = ctx->opt_v3_l2promo;
-    const long long n_elems = (long long)(a.nb - 1) * a.stride + a.g.N;
-    if (int e = v3_make_map(&a.tm_src, &a.sh_src, a.src, n_elems, a.g.n1, C::BW, C::BH, l2p))
+    // the maps span the ghost planes around the owned range of every block
+    const long long below   = (long long)a.g.gh_lo * a.g.plane;
+    const long long n_elems = (long long)(a.nb - 1) * a.stride + a.g.N + (long long)(a.g.gh_lo + a.g.gh_hi) * a.g.plane;
+    a.L_lo = a.g.L_lo, a.L_hi = a.g.L_hi, a.zo0 = a.g.zo0, a.gh_lo = a.g.gh_lo;
+    if (int e = v3_make_map(&a.tm_src, &a.sh_src, a.src - below, n_elems, a.g.n1, C::BW, C::BH, l2p))
       return e;
     a.tm_o0 = a.tm_src, a.tm_o1 = a.tm_src, a.sh_o0 = a.sh_o1 = 0;
     if (NBC > 1 && a.km) // the second staged plane comes from block b of the vector passed as x_old
-      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, a.x_old, n_elems, a.g.n1, C::BW, C::BH, l2p))
+      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, a.x_old - below, n_elems, a.g.n1, C::BW, C::BH, l2p))
         return e;
     const double *o0 = (MODE == V2_RESIDUAL) ? a.rhs : (MODE == V2_CHEB_OWN ? a.x_old : nullptr);
     if (o0 != nullptr)
-      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, o0, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
+      if (int e = v3_make_map(&a.tm_o0, &a.sh_o0, o0 - below, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
         return e;
     if (MODE == V2_CHEB_OWN)
-      if (int e = v3_make_map(&a.tm_o1, &a.sh_o1, a.rhs, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
+      if (int e = v3_make_map(&a.tm_o1, &a.sh_o1, a.rhs - below, n_elems, a.g.n1, C::OW, C::OY / 2, l2p))
         return e;
     // Schedules (option "v3_schedule"): 2 (default) work queue of (block, layer range, column) items with the partial sums
     // of the shared vertex planes exchanged between neighbouring ranges (no recomputation, any number of items per CTA);
@@ -1024,7 +1032,8 @@ namespace spirk
     long long       grid  = std::max(1LL, std::min(ctx->opt_v3_grid > 0 ? (long long)ctx->opt_v3_grid : slots, a.W / 4));
     a.lock_nch = 0, a.lock_len = 0, a.dyn = 0, a.n_items = 0, a.sched = nullptr, a.state = nullptr, a.carry = nullptr;
     const long long cols  = (long long)a.nb * a.ntx * a.nty;
-    const int       force = ctx->opt_v3_schedule;
+    const int       nloc  = a.g.L_hi - a.g.L_lo; // cell layers of this slab
+    const int       force = (a.g.col_size > 1) ? 2 : ctx->opt_v3_schedule; // (z-slabs: the work queue only)
     if (force < 0 || force == 2)
       {
         // layers per item: as short as possible while the items do not outnumber the CTA slots, 8 at most (an item costs a
@@ -1034,13 +1043,13 @@ namespace spirk
           len = ctx->opt_v3_chunk;
         else
           for (int c = 1; c < 8; c *= 2)
-            if (cols * ((a.g.nc + c - 1) / c) <= slots)
+            if (cols * ((nloc + c - 1) / c) <= slots)
               {
                 len = c;
                 break;
               }
-        len = std::max(1, std::min(len, a.g.nc));
-        a.lock_len = len, a.lock_nch = (a.g.nc + len - 1) / len;
+        len = std::max(1, std::min(len, nloc));
+        a.lock_len = len, a.lock_nch = (nloc + len - 1) / len;
         a.dyn      = 1;
         a.n_items  = (int)(cols * a.lock_nch);
         if (int e = ensure_v3_queue(ctx, (size_t)a.n_items, (size_t)a.n_items * C::NY * NPT))

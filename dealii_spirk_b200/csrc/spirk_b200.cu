@@ -151,6 +151,9 @@ namespace spirk
       return set_error(SPIRK_ERR_INVALID, "bad level descriptor");
     if (l->degree < 1 || l->degree > SPIRK_MAX_DEGREE)
       return set_error(SPIRK_ERR_UNSUPPORTED, "degree must be 1..6");
+    const int col_size = (l->slab >> 8) & 0xff, col_rank = l->slab & 0xff;
+    if (col_size > 1 && (l->dim != 3 || l->n_cells_1d % col_size != 0 || col_rank >= col_size))
+      return set_error(SPIRK_ERR_INVALID, "z-slab levels: 3-D, n_cells_1d a multiple of the number of slabs, rank < size");
     return SPIRK_OK;
   }
 
@@ -227,6 +230,8 @@ namespace spirk
   // dst = A src with the variant selected by the context; mode-specific fused paths in op_v2
   static int apply_any(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, double *dst, const double *src, long long stride)
   {
+    if (g.col_size > 1)
+      return set_error(SPIRK_ERR_UNSUPPORTED, "z-slab levels need the plane-streaming cell operator (3-D, Q4, >= 8 cells per direction)");
     const OpDev od      = make_opdev(g, op);
     const bool  coupled = op->kind == SPIRK_OP_COUPLED;
     int         st      = SPIRK_OK;
@@ -710,19 +715,44 @@ static Sweep1D make_sweep(int d, int ex, int ey, int ez, int n_in, int ncc)
   w.d = d, w.ex = ex, w.ey = ey, w.ez = ez, w.n_in = n_in, w.ncc = ncc;
   w.N_out = (long long)ex * ey * ez;
   w.N_in  = w.N_out / (d == 0 ? ex : (d == 1 ? ey : ez)) * n_in;
+  w.ec0 = 0, w.in_z0 = 0, w.out_z0 = 0;
   return w;
+}
+
+// what the two transfers share: extents, slab ranges and launch shapes
+struct TransferShape
+{
+  Geo       g;                // fine level (maybe a z-slab)
+  int       ncc, nf, ncn;     // coarse cells / fine nodes / coarse nodes per direction (whole mesh)
+  int       ec0, nec;         // coarse cells of this slab in z
+  int       zf_owned;         // owned fine planes
+  int       zc0;              // global index of local plane 0 of the coarse vector as the caller passes it
+};
+static int transfer_shape(const spirk_level *lf, TransferShape &t)
+{
+  if (int e = check_level(lf))
+    return e;
+  if (lf->n_cells_1d % 2)
+    return set_error(SPIRK_ERR_INVALID, "transfer: the fine level needs an even number of cells");
+  t.g   = make_geo(lf);
+  t.ncc = t.g.nc / 2, t.nf = t.g.n1, t.ncn = t.g.k * t.ncc + 1;
+  if (t.g.col_size > 1 && (t.g.L_lo % 2 || t.g.L_hi % 2))
+    return set_error(SPIRK_ERR_INVALID, "transfer: a z-slab needs an even number of cell layers");
+  t.ec0 = t.g.L_lo / 2, t.nec = (t.g.L_hi - t.g.L_lo) / 2;
+  t.zf_owned = (t.g.dim == 3) ? t.g.zo1 - t.g.zo0 : 1;
+  t.zc0      = (t.g.col_size > 1 && !t.g.coarse_replicated) ? t.g.k * t.ec0 : 0;
+  return SPIRK_OK;
 }
 
 int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, double *fine, long long fs, const double *coarse,
                             long long cs)
 {
-  if (int e = check_level(lf))
+  TransferShape t;
+  if (int e = transfer_shape(lf, t))
     return e;
-  if (lf->n_cells_1d % 2)
-    return set_error(SPIRK_ERR_INVALID, "prolongate: fine level needs an even number of cells");
-  const Geo g   = make_geo(lf);
-  const int ncc = g.nc / 2, nf = g.n1, ncn = g.k * ncc + 1;
-  if (ctx->opt_transfer_variant == 1)
+  const Geo &g   = t.g;
+  const int  ncc = t.ncc, nf = t.nf, ncn = t.ncn;
+  if (ctx->opt_transfer_variant == 1 && g.col_size == 1)
     {
       const long long ncells = (g.dim == 3 ? (long long)ncc * ncc * ncc : (long long)ncc * ncc) * nb;
       const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 16);
@@ -737,24 +767,28 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
       SPIRK_LAUNCH_CHECK(ctx);
       return SPIRK_OK;
     }
-  // expand z, then y (one thread per entry, lanes along x), then x from rows staged in shared memory, adding into the fine vector
+  // expand z, then y (one thread per coarse cell and entry of the other directions, lanes along x), then x from rows staged in
+  // shared memory, adding into the fine vector.  z-slab: the coarse cells of this slab produce exactly its owned fine planes
+  // (they read one coarse ghost plane above).
   constexpr int RPB = 8;
-  const auto grid_1d = [&](const Sweep1D &w) {
-    return dim3((unsigned)(((w.d == 1 ? w.ex * w.ez : w.ex * w.ey) + 255) / 256), (unsigned)ncc, (unsigned)nb);
+  const auto grid_1d = [&](const Sweep1D &w, int cells) {
+    return dim3((unsigned)(((w.d == 1 ? w.ex * w.ez : w.ex * w.ey) + 255) / 256), (unsigned)cells, (unsigned)nb);
   };
-  const dim3      blk_x(32, RPB);
-  const size_t    smem_x = sizeof(double) * ((size_t)RPB * ncn + (2 * g.k + 1) * (g.k + 1));
+  const dim3   blk_x(32, RPB);
+  const size_t smem_x = sizeof(double) * ((size_t)RPB * ncn + (2 * g.k + 1) * (g.k + 1));
   if (g.dim == 3)
     {
-      const Sweep1D wz = make_sweep(2, ncn, ncn, nf, ncn, ncc), wy = make_sweep(1, ncn, nf, nf, ncn, ncc);
+      const int zf = t.zf_owned;
+      Sweep1D   wz = make_sweep(2, ncn, ncn, zf, ncn, ncc), wy = make_sweep(1, ncn, nf, zf, ncn, ncc);
+      wz.ec0 = t.ec0, wz.in_z0 = t.zc0, wz.out_z0 = g.zo0;
       if (int e = ensure_scratch(ctx, (size_t)nb * (wz.N_out + wy.N_out)))
         return e;
       double *t2 = ctx->d_scratch, *t1 = ctx->d_scratch + (size_t)nb * wz.N_out;
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wz), 256, 0, ctx->stream>>>(wz, t2, wz.N_out, coarse, cs)));
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wz, t.nec), 256, 0, ctx->stream>>>(wz, t2, wz.N_out, coarse, cs)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, t2, wz.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy, ncc), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, t2, wz.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
-      const long long rpb = (long long)nf * nf, rows = rpb * nb;
+      const long long rpb = (long long)nf * zf, rows = rpb * nb;
       SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, fine, fs, t1, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
@@ -765,7 +799,7 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
       if (int e = ensure_scratch(ctx, (size_t)nb * wy.N_out))
         return e;
       double *t1 = ctx->d_scratch;
-      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, coarse, cs)));
+      SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy, ncc), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, coarse, cs)));
       SPIRK_LAUNCH_CHECK(ctx);
       const long long rpb = nf, rows = rpb * nb;
       SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
@@ -778,13 +812,12 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
 int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coarse, long long cs, const double *fine,
                       long long fs)
 {
-  if (int e = check_level(lf))
+  TransferShape t;
+  if (int e = transfer_shape(lf, t))
     return e;
-  if (lf->n_cells_1d % 2)
-    return set_error(SPIRK_ERR_INVALID, "restrict: fine level needs an even number of cells");
-  const Geo g   = make_geo(lf);
-  const int ncc = g.nc / 2, nf = g.n1, ncn = g.k * ncc + 1;
-  if (ctx->opt_transfer_variant == 1)
+  const Geo &g   = t.g;
+  const int  ncc = t.ncc, nf = t.nf, ncn = t.ncn;
+  if (ctx->opt_transfer_variant == 1 && g.col_size == 1)
     {
       // cell-based variant (atomics into a zeroed coarse vector; kept for A/B measurements)
       spirk_level lc = *lf;
@@ -805,27 +838,31 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
       SPIRK_LAUNCH_CHECK(ctx);
       return SPIRK_OK;
     }
-  // contract x (fine rows staged in shared memory), then y, then z (one thread per entry, lanes along x): every coarse
-  // entry is written exactly once
+  // contract x (fine rows staged in shared memory), then y, then z: every coarse entry is written exactly once.  z-slab: x
+  // and y run over the owned fine planes and the ghost planes around them (2k below, 1 above), z produces the coarse planes
+  // of this slab's coarse cells.
   constexpr int RPB = 8;
-  const auto grid_1d = [&](const Sweep1D &w) {
-    return dim3((unsigned)(((w.d == 1 ? w.ex * w.ez : w.ex * w.ey) + 255) / 256), (unsigned)ncc, (unsigned)nb);
+  const auto grid_1d = [&](const Sweep1D &w, int cells) {
+    return dim3((unsigned)(((w.d == 1 ? w.ex * w.ez : w.ex * w.ey) + 255) / 256), (unsigned)cells, (unsigned)nb);
   };
-  const dim3      blk_x(32, RPB);
-  const size_t    smem_x = sizeof(double) * ((size_t)RPB * (nf + ncn));
+  const dim3   blk_x(32, RPB);
+  const size_t smem_x = sizeof(double) * ((size_t)RPB * (nf + ncn));
   if (g.dim == 3)
     {
-      const Sweep1D wx = make_sweep(0, ncn, nf, nf, nf, ncc), wy = make_sweep(1, ncn, ncn, nf, nf, ncc), wz = make_sweep(2, ncn, ncn, ncn, nf, ncc);
+      const int       zin = g.gh_lo + t.zf_owned + g.gh_hi; // fine planes in memory per block
+      const Sweep1D   wx = make_sweep(0, ncn, nf, zin, nf, ncc), wy = make_sweep(1, ncn, ncn, zin, nf, ncc);
+      Sweep1D         wz = make_sweep(2, ncn, ncn, ncn, zin, ncc);
+      wz.ec0 = t.ec0, wz.in_z0 = g.zo0 - g.gh_lo, wz.out_z0 = t.zc0;
       if (int e = ensure_scratch(ctx, (size_t)nb * (wx.N_out + wy.N_out)))
         return e;
       double         *t1 = ctx->d_scratch, *t2 = ctx->d_scratch + (size_t)nb * wx.N_out;
-      const long long rpb = (long long)nf * nf, rows = rpb * nb;
+      const long long rpb = (long long)nf * zin, rows = rpb * nb;
       SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
-                              nf, ncc, rows, rpb, t1, wx.N_out, fine, fs)));
+                              nf, ncc, rows, rpb, t1, wx.N_out, fine - (long long)g.gh_lo * g.plane, fs)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, t2, wy.N_out, t1, wx.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy, ncc), 256, 0, ctx->stream>>>(wy, t2, wy.N_out, t1, wx.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wz), 256, 0, ctx->stream>>>(wz, coarse, cs, t2, wy.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wz, t.nec), 256, 0, ctx->stream>>>(wz, coarse, cs, t2, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
   else
@@ -838,7 +875,7 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
       SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, t1, wx.N_out, fine, fs)));
       SPIRK_LAUNCH_CHECK(ctx);
-      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy), 256, 0, ctx->stream>>>(wy, coarse, cs, t1, wx.N_out)));
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy, ncc), 256, 0, ctx->stream>>>(wy, coarse, cs, t1, wx.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
     }
   return SPIRK_OK;
@@ -940,6 +977,73 @@ int spirk_vec_sum(spirk_ctx *ctx, const double *x, long long n, double *host_res
   k_sum<<<grid, RT, 0, ctx->stream>>>(x, n, ctx->d_partials);
   SPIRK_LAUNCH_CHECK(ctx);
   return finish_reduction(ctx, 1, grid, host_result);
+}
+
+static inline dim3 reduction_grid_strided(const spirk_ctx *ctx, long long n, int nb)
+{
+  long long blocks = (n + RT * 4 - 1) / (RT * 4);
+  return dim3((unsigned)std::max<long long>(1, std::min<long long>(blocks, std::max(1, ctx->n_partials / nb))), (unsigned)nb);
+}
+int spirk_vec_dot_strided(spirk_ctx *ctx, const double *x, const double *y, long long n, int nb, long long stride, double *host_result)
+{
+  if (nb < 1 || nb > SPIRK_MAX_BLOCKS)
+    return set_error(SPIRK_ERR_INVALID, "dot_strided: nb");
+  const dim3 grid = reduction_grid_strided(ctx, n, nb);
+  k_dot_strided<<<grid, RT, 0, ctx->stream>>>(x, y, n, stride, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return finish_reduction(ctx, 1, (int)(grid.x * grid.y), host_result);
+}
+int spirk_vec_sum_strided(spirk_ctx *ctx, const double *x, long long n, int nb, long long stride, double *host_result)
+{
+  if (nb < 1 || nb > SPIRK_MAX_BLOCKS)
+    return set_error(SPIRK_ERR_INVALID, "sum_strided: nb");
+  const dim3 grid = reduction_grid_strided(ctx, n, nb);
+  k_sum_strided<<<grid, RT, 0, ctx->stream>>>(x, n, stride, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return finish_reduction(ctx, 1, (int)(grid.x * grid.y), host_result);
+}
+int spirk_vec_add_and_dot_strided(spirk_ctx *ctx, double *v, double a, const double *V, const double *W, long long n, int nb,
+                                  long long stride, double *host_result)
+{
+  if (nb < 1 || nb > SPIRK_MAX_BLOCKS)
+    return set_error(SPIRK_ERR_INVALID, "add_and_dot_strided: nb");
+  const dim3 grid = reduction_grid_strided(ctx, n, nb);
+  k_add_and_dot_strided<<<grid, RT, 0, ctx->stream>>>(v, a, nullptr, V, W, n, stride, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  return finish_reduction(ctx, 1, (int)(grid.x * grid.y), host_result);
+}
+int spirk_gmres_mgs_strided(spirk_ctx *ctx, double *vv, const double *const *basis, int dim, long long n, int nb, long long stride,
+                            double *h, double *norm)
+{
+  if (dim < 1 || dim > 62 || nb < 1 || nb > SPIRK_MAX_BLOCKS)
+    return set_error(SPIRK_ERR_INVALID, "gmres_mgs_strided: dim / nb");
+  const dim3 grid = reduction_grid_strided(ctx, n, nb);
+  const int  np   = (int)(grid.x * grid.y);
+  auto       finish = [&](int slot) -> int {
+    k_finish<<<1, RT, 0, ctx->stream>>>(ctx->d_partials, np, ctx->d_result + slot);
+    SPIRK_LAUNCH_CHECK(ctx);
+    if (ctx->reduction_comm)
+      return spirk_comm_allreduce_sum(ctx, ctx->reduction_comm, ctx->d_result + slot, 1);
+    return SPIRK_OK;
+  };
+  k_dot_strided<<<grid, RT, 0, ctx->stream>>>(vv, basis[0], n, stride, ctx->d_partials);
+  SPIRK_LAUNCH_CHECK(ctx);
+  if (int e = finish(0))
+    return e;
+  for (int i = 1; i <= dim; ++i)
+    {
+      k_add_and_dot_strided<<<grid, RT, 0, ctx->stream>>>(vv, 0.0, ctx->d_result + (i - 1), basis[i - 1], (i < dim) ? basis[i] : vv, n,
+                                                           stride, ctx->d_partials);
+      SPIRK_LAUNCH_CHECK(ctx);
+      if (int e = finish(i))
+        return e;
+    }
+  SPIRK_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, (dim + 1) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < dim; ++i)
+    h[i] = ctx->h_result[i];
+  *norm = std::sqrt(ctx->h_result[dim]);
+  return SPIRK_OK;
 }
 
 int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *const *basis, int dim, long long n, double *h, double *norm)
@@ -1050,12 +1154,21 @@ int spirk_problem_interpolate_solution(spirk_ctx *ctx, const spirk_level *lvl, d
 
 int spirk_problem_error_norms(spirk_ctx *ctx, const spirk_level *lvl, const double *u, double t, double *l2, double *linf)
 {
+  double l2sq = 0;
+  if (int e = spirk_problem_error_norms_partial(ctx, lvl, u, t, &l2sq, linf))
+    return e;
+  *l2 = std::sqrt(l2sq);
+  return SPIRK_OK;
+}
+
+int spirk_problem_error_norms_partial(spirk_ctx *ctx, const spirk_level *lvl, const double *u, double t, double *l2, double *linf)
+{
   if (int e = check_level(lvl))
     return e;
   const Geo    g  = make_geo(lvl);
   const double ft = (1.0 + std::sin(M_PI * t)) * std::exp(-0.5 * t);
   SPIRK_CUDA(cudaMemsetAsync(ctx->d_result, 0, 2 * sizeof(double), ctx->stream));
-  const long long ncells = (g.dim == 3) ? (long long)g.nc * g.nc * g.nc : (long long)g.nc * g.nc;
+  const long long ncells = (g.dim == 3) ? (long long)g.nc * g.nc * (g.L_hi - g.L_lo) : (long long)g.nc * g.nc;
   const int       grid   = (int)std::min<long long>(ncells, (long long)ctx->n_sms * 8);
   if (g.dim == 3)
     {
@@ -1068,7 +1181,7 @@ int spirk_problem_error_norms(spirk_ctx *ctx, const spirk_level *lvl, const doub
   SPIRK_LAUNCH_CHECK(ctx);
   SPIRK_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
-  *l2   = std::sqrt(ctx->h_result[0]);
+  *l2   = ctx->h_result[0]; // the SQUARE of the L2 norm over this level's cells (a z-slab: its share)
   *linf = ctx->h_result[1];
   return SPIRK_OK;
 }
@@ -1133,6 +1246,83 @@ int spirk_comm_allreduce_sum(spirk_ctx *ctx, spirk_comm *c, double *buf, long lo
   if (c->n_ranks == 1)
     return SPIRK_OK;
   SPIRK_NCCL(nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, c->comm, ctx->stream));
+  ctx->launches++;
+  return SPIRK_OK;
+}
+int spirk_comm_split(spirk_ctx *ctx, spirk_comm *c, int color, int key, spirk_comm **out)
+{
+  SPIRK_CUDA(cudaSetDevice(ctx->device));
+  // sizes / ranks of the new communicator: all ranks exchange (color, key)
+  std::vector<int> mine = {color, key}, all((size_t)2 * c->n_ranks);
+  int             *d    = nullptr;
+  SPIRK_CUDA(cudaMalloc(&d, sizeof(int) * 2 * (c->n_ranks + 1)));
+  SPIRK_CUDA(cudaMemcpyAsync(d, mine.data(), 2 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (c->n_ranks > 1)
+    SPIRK_NCCL(nccl.AllGather(d, d + 2, 2, ncclInt, c->comm, ctx->stream));
+  else
+    SPIRK_CUDA(cudaMemcpyAsync(d + 2, d, 2 * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+  SPIRK_CUDA(cudaMemcpyAsync(all.data(), d + 2, sizeof(int) * 2 * c->n_ranks, cudaMemcpyDeviceToHost, ctx->stream));
+  SPIRK_CUDA(cudaStreamSynchronize(ctx->stream));
+  SPIRK_CUDA(cudaFree(d));
+  spirk_comm *s = new spirk_comm();
+  for (int r = 0; r < c->n_ranks; ++r)
+    if (all[2 * r] == color)
+      {
+        if (all[2 * r + 1] < key || (all[2 * r + 1] == key && r < c->rank))
+          s->rank++;
+        s->n_ranks++;
+      }
+  s->n_ranks -= 1; // (the struct starts at n_ranks = 1)
+  if (c->n_ranks > 1)
+    {
+      const NcclApi &api = nccl_api();
+      ncclResult_t   r   = api.CommSplit(c->comm, color, key, &s->comm, nullptr);
+      if (r != ncclSuccess)
+        {
+          delete s;
+          return set_error(SPIRK_ERR_COMM, std::string("ncclCommSplit: ") + api.GetErrorString(r));
+        }
+    }
+  *out = s;
+  return SPIRK_OK;
+}
+int spirk_comm_allreduce_max(spirk_ctx *ctx, spirk_comm *c, double *buf, long long n)
+{
+  if (c->n_ranks == 1)
+    return SPIRK_OK;
+  SPIRK_NCCL(nccl.AllReduce(buf, buf, n, ncclDouble, ncclMax, c->comm, ctx->stream));
+  ctx->launches++;
+  return SPIRK_OK;
+}
+int spirk_halo_exchange(spirk_ctx *ctx, spirk_comm *c, const spirk_level *lvl, int nb, double *vec, long long stride, int n_lo, int n_hi)
+{
+  if (int e = check_level(lvl))
+    return e;
+  const Geo g = make_geo(lvl);
+  if (g.col_size == 1)
+    return SPIRK_OK;
+  if (!c || c->n_ranks != g.col_size || c->rank != g.col_rank || n_lo < 0 || n_hi < 0 || n_lo > g.gh_lo || n_hi > g.gh_hi ||
+      n_lo > g.zo1 - g.zo0 || n_hi > g.zo1 - g.zo0)
+    return set_error(SPIRK_ERR_INVALID, "halo_exchange: communicator / ghost depth do not match the level");
+  const long long own = g.N;
+  // my ghost planes below = the top n_lo owned planes of the slab below; my ghost planes above = the bottom n_hi owned planes
+  // of the slab above (the top slab also owns the top plane of the domain: its top n_lo planes END at k L_hi of ... its own
+  // last plane is irrelevant to a neighbour, and it has no upper neighbour)
+  const bool      has_lo = g.col_rank > 0, has_hi = g.col_rank + 1 < g.col_size;
+  SPIRK_NCCL(nccl.GroupStart());
+  for (int b = 0; b < nb; ++b)
+    {
+      double *o = vec + b * stride;
+      if (has_hi && n_lo > 0) // my top n_lo owned planes -> ghost planes below of the slab above
+        SPIRK_NCCL(nccl.Send(o + own - (long long)n_lo * g.plane, (size_t)n_lo * g.plane, ncclDouble, c->rank + 1, c->comm, ctx->stream));
+      if (has_lo && n_lo > 0)
+        SPIRK_NCCL(nccl.Recv(o - (long long)n_lo * g.plane, (size_t)n_lo * g.plane, ncclDouble, c->rank - 1, c->comm, ctx->stream));
+      if (has_lo && n_hi > 0) // my bottom n_hi owned planes -> ghost planes above of the slab below
+        SPIRK_NCCL(nccl.Send(o, (size_t)n_hi * g.plane, ncclDouble, c->rank - 1, c->comm, ctx->stream));
+      if (has_hi && n_hi > 0)
+        SPIRK_NCCL(nccl.Recv(o + own, (size_t)n_hi * g.plane, ncclDouble, c->rank + 1, c->comm, ctx->stream));
+    }
+  SPIRK_NCCL(nccl.GroupEnd());
   ctx->launches++;
   return SPIRK_OK;
 }

@@ -36,7 +36,7 @@ namespace
 struct spirk_run
 {
   std::unique_ptr<Device>                          device;
-  spirk_comm                                      *comm = nullptr;
+  spirk_comm                                      *comm = nullptr, *comm_row = nullptr, *comm_col = nullptr;
   HeatEquation::Parameters                         params;
   ConvergenceTable                                 table;
   std::unique_ptr<HeatEquation::ProblemBase>       problem;
@@ -44,6 +44,10 @@ struct spirk_run
   ~spirk_run()
   {
     problem.reset();
+    if (comm_row)
+      spirk_comm_destroy(comm_row);
+    if (comm_col)
+      spirk_comm_destroy(comm_col);
     if (comm)
       spirk_comm_destroy(comm);
     device.reset();
@@ -68,17 +72,41 @@ int spirk_host_create(const char *json, int is_path, int dim, int device, const 
       run->params.parse_text(json);
     run->device.reset(new Device(device));
     TimeIntegrationSchemes::RowComm row;
+    HeatEquation::ColumnComm        col;
     if (nccl_id128 && world_size > 1)
       {
         SPIRK_CHECK(spirk_comm_create(run->device->ctx(), nccl_id128, world_size, world_rank, &run->comm));
-        row = TimeIntegrationSchemes::RowComm(run->comm);
+        // The reference's rectangular process grid (main.cc:3660-3698): size_x = stage ranks (IRKStages for spirk, the
+        // conjugate pairs for complex_spirk*), the remaining factor of the world size = space ranks (z-slabs of the mesh).
+        // With fewer ranks than stages every rank takes several stages and there is one column.
+        const std::string &scheme = run->params.time_integration_scheme;
+        const int          q      = (int)run->params.irk_stages;
+        int                size_x = (scheme == "spirk") ? q : ((scheme == "complex_spirk" || scheme == "complex_spirk_batched") ? (q + 1) / 2 : 1);
+        if (world_size < size_x || world_size % size_x != 0)
+          {
+            if (size_x % world_size != 0)
+              throw Error("the number of ranks must be a multiple or a divisor of the number of stage ranks");
+            size_x = world_size; // several stages per rank, no spatial partition
+          }
+        const int size_y = world_size / size_x;
+        if (size_y == 1)
+          row = TimeIntegrationSchemes::RowComm(run->comm);
+        else
+          {
+            // row-major lex_to_pair (main.cc:281-293): stage index = rank % size_x, slab = rank / size_x
+            const int ix = world_rank % size_x, iy = world_rank / size_x;
+            SPIRK_CHECK(spirk_comm_split(run->device->ctx(), run->comm, /*color=*/iy, /*key=*/ix, &run->comm_row));
+            SPIRK_CHECK(spirk_comm_split(run->device->ctx(), run->comm, /*color=*/ix, /*key=*/iy, &run->comm_col));
+            row      = TimeIntegrationSchemes::RowComm(run->comm_row, size_x > 1 ? run->comm : nullptr);
+            col.comm = run->comm_col, col.rank = iy, col.size = size_y;
+          }
       }
     run->verbose        = verbose && world_rank == 0;
     std::ostream *pcout = run->verbose ? &std::cout : nullptr;
     if (dim == 2)
-      run->problem.reset(new HeatEquation::Problem<2>(run->params, *run->device, row, run->table, pcout));
+      run->problem.reset(new HeatEquation::Problem<2>(run->params, *run->device, row, run->table, pcout, col));
     else
-      run->problem.reset(new HeatEquation::Problem<3>(run->params, *run->device, row, run->table, pcout));
+      run->problem.reset(new HeatEquation::Problem<3>(run->params, *run->device, row, run->table, pcout, col));
     *out = run.release();
   });
 }
@@ -136,6 +164,10 @@ int spirk_host_get_scalar(spirk_run *run, const char *key, double *value)
     const auto       &p  = *run->problem;
     if (k == "n_dofs")
       *value = (double)p.n_dofs;
+    else if (k == "n_dofs_owned")
+      *value = (double)p.n_dofs_owned;
+    else if (k == "first_owned")
+      *value = (double)p.first_owned;
     else if (k == "time")
       *value = p.time;
     else if (k == "timestep_number")

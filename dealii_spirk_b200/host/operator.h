@@ -17,7 +17,22 @@ namespace spirk_host
   {
     Device     *device = nullptr;
     spirk_level level{};
-    long long   n_dofs() const { return spirk_level_n_dofs(&level); }
+    spirk_comm *column_comm = nullptr; // the space communicator of a z-slab level (the triangulation's communicator, main.cc:3027)
+    long long   n_dofs() const { return spirk_level_n_dofs(&level); } // locally owned
+    bool        partitioned() const { return ((level.slab >> 8) & 0xff) > 1; }
+    int         n1() const { return level.degree * level.n_cells_1d + 1; }
+    // update_ghost_values (operator.h:301-306): n_lo planes below / n_hi above the owned range of every block of v
+    void exchange_ghosts(double *v, int nb, long long stride, int n_lo, int n_hi) const
+    {
+      if (partitioned())
+        SPIRK_CHECK(spirk_halo_exchange(device->ctx(), column_comm, &level, nb, v, stride, n_lo, n_hi));
+    }
+    void exchange_ghosts(const Vector &v, int n_lo, int n_hi) const
+    {
+      exchange_ghosts(const_cast<double *>(v.data()), (int)v.n_blocks(), v.stride(), n_lo, n_hi);
+    }
+    // what the cell operator reads beyond the owned planes: one cell layer below, one node plane above
+    void exchange_ghosts_for_operator(const Vector &v) const { exchange_ghosts(v, level.degree, 1); }
   };
 
   inline spirk_opdesc real_opdesc(int nb, const double *mass, const double *laplace)
@@ -108,13 +123,24 @@ namespace spirk_host
   public:
     // (dof_handler, constraints, quadrature) of the reference collapse to (device, degree, refinement):
     // hypercube, FE_Q(degree), QGauss(degree+1), homogeneous Dirichlet (main.cc:3038-3039, 3400-3411)
-    MassLaplaceOperatorMatrixFree(Device &device, const unsigned int fe_degree, const unsigned int n_refinements)
+    // column_comm / col_rank / col_size: the z-slab of a spatially partitioned level (the reference's triangulation lives
+    // on comm_column, main.cc:3027, 3478); coarse_replicated: the next coarser level is held in full by every rank
+    MassLaplaceOperatorMatrixFree(Device &device, const unsigned int fe_degree, const unsigned int n_refinements,
+                                  spirk_comm *column_comm = nullptr, const int col_rank = 0, const int col_size = 1,
+                                  const bool coarse_replicated = false)
     {
       matrix_free.device            = &device;
       matrix_free.level.dim         = dim;
       matrix_free.level.degree      = fe_degree;
       matrix_free.level.n_cells_1d  = 1 << n_refinements;
-      matrix_free.level.reserved    = 0;
+      matrix_free.level.slab        = (col_size > 1) ? SPIRK_SLAB(col_rank, col_size, coarse_replicated) : 0;
+      if (col_size > 1)
+        {
+          matrix_free.column_comm = column_comm;
+          const long long plane   = (long long)matrix_free.n1() * matrix_free.n1();
+          device.register_padding(matrix_free.n_dofs(), SPIRK_SLAB_PAD_LO(fe_degree) * plane, SPIRK_SLAB_PAD_HI * plane);
+          device.column_comm = column_comm;
+        }
     }
 
     const MatrixFree &get_matrix_free() const override { return matrix_free; }
@@ -132,7 +158,8 @@ namespace spirk_host
     void vmult(VectorType &dst, const VectorType &src) const override
     {
       const spirk_opdesc d = descriptor();
-      SPIRK_CHECK(spirk_op_apply(matrix_free.device->ctx(), &matrix_free.level, &d, dst.data(), src.data(), dst.block_size()));
+      matrix_free.exchange_ghosts_for_operator(src);
+      SPIRK_CHECK(spirk_op_apply(matrix_free.device->ctx(), &matrix_free.level, &d, dst.data(), src.data(), dst.stride()));
     }
 
     void vmult_add(VectorType &, const VectorType &) const override
@@ -238,7 +265,8 @@ namespace spirk_host
         throw Error("ComplexMassLaplaceOperatorMatrixFree: scalar-operator path needs vmult_add (ExcNotImplemented, "
                     "ref operator.h:313-316); the reference never enables it (main.cc:3256-3258)");
       const spirk_opdesc d = descriptor();
-      SPIRK_CHECK(spirk_op_apply(matrix_free.device->ctx(), &matrix_free.level, &d, dst.data(), src.data(), dst.block_size()));
+      matrix_free.exchange_ghosts_for_operator(src);
+      SPIRK_CHECK(spirk_op_apply(matrix_free.device->ctx(), &matrix_free.level, &d, dst.data(), src.data(), dst.stride()));
     }
     void Tvmult(BlockVectorType &, const BlockVectorType &) const override { throw Error("Tvmult: ExcNotImplemented"); }
 
@@ -301,7 +329,8 @@ namespace spirk_host
     void vmult(BlockVectorType &dst, const BlockVectorType &src) const override
     {
       const spirk_opdesc d = descriptor();
-      SPIRK_CHECK(spirk_op_apply(matrix_free.device->ctx(), &matrix_free.level, &d, dst.data(), src.data(), dst.block_size()));
+      matrix_free.exchange_ghosts_for_operator(src);
+      SPIRK_CHECK(spirk_op_apply(matrix_free.device->ctx(), &matrix_free.level, &d, dst.data(), src.data(), dst.stride()));
     }
     void Tvmult(BlockVectorType &, const BlockVectorType &) const override { throw Error("Tvmult: ExcNotImplemented"); }
 

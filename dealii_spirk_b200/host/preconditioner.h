@@ -125,7 +125,7 @@ namespace spirk_host
       {
         std::vector<double> one(dinv.n_blocks(), 1.0);
         SPIRK_CHECK(spirk_vec_scale_pointwise(dst.ctx(), dinv.n_blocks(), dinv.block_size(), dst.data(), dinv.data(), src.data(),
-                                              dinv.block_size(), one.data()));
+                                              dinv.stride(), one.data()));
       }
     };
 
@@ -139,7 +139,9 @@ namespace spirk_host
     struct MGLevel
     {
       spirk_level         level{};
-      long long           n = 0;
+      MatrixFree          mf;          // the level's mesh (a z-slab of it on partitioned levels) and its column communicator
+      long long           n = 0;      // locally owned entries per block
+      long long           stride = 0; // distance between the blocks of the work vectors (ghost planes on z-slab levels)
       Vector              dinv;
       std::vector<double> theta, delta; // per block
       std::vector<double> max_eigenvalue, min_eigenvalue;
@@ -172,8 +174,13 @@ namespace spirk_host
       void allocate_work_vectors()
       {
         for (auto &L : levels)
-          for (Vector *v : {&L.defect, &L.solution, &L.t, &L.d, &L.tmp})
-            v->reinit(*dev, L.n, nb);
+          {
+            for (Vector *v : {&L.defect, &L.solution, &L.t, &L.d, &L.tmp})
+              v->reinit(*dev, L.n, nb);
+            L.stride = L.defect.stride();
+            if (L.mf.partitioned())
+              use_graph = false; // (the halo exchanges are NCCL calls; the V-cycle of a partitioned hierarchy runs eagerly)
+          }
       }
 
       // PreconditionChebyshev::vmult on level l (zero initial guess), result in x (A7)
@@ -199,7 +206,7 @@ namespace spirk_host
         // iterations 0 and 1 in one pass over b when the smoother's diagonal is the level operator's own
         const bool fuse_first = own_dinv && degree >= 2 && any && fuse_first_iterations();
         if (!fuse_first)
-          SPIRK_CHECK(spirk_vec_scale_pointwise(dev->ctx(), nb, L.n, x.data(), L.dinv.data(), b.data(), L.n, f.data()));
+          SPIRK_CHECK(spirk_vec_scale_pointwise(dev->ctx(), nb, L.n, x.data(), L.dinv.data(), b.data(), L.stride, f.data()));
         if (degree < 2 || !any)
           return;
         double *cur = x.data(), *old = L.tmp.data();
@@ -212,15 +219,23 @@ namespace spirk_host
                 rhok[i] = rhokp;
               }
             // x_new overwrites the x_old buffer (deal.II swaps solution / solution_old)
+            // the vector the cell operator is applied to needs its ghost planes (z-slab levels)
+            const int kd = L.level.degree;
             if (k == 0 && fuse_first)
-              SPIRK_CHECK(spirk_op_cheb_first(dev->ctx(), &L.level, &op, cur, old, b.data(), L.n, f.data(), f1.data(), f2.data()));
+              {
+                L.mf.exchange_ghosts(const_cast<double *>(b.data()), nb, L.stride, kd, 1);
+                SPIRK_CHECK(spirk_op_cheb_first(dev->ctx(), &L.level, &op, cur, old, b.data(), L.stride, f.data(), f1.data(), f2.data()));
+              }
             else
-              SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
-                                             own_dinv ? nullptr : L.dinv.data(), L.n, f1.data(), f2.data()));
+              {
+                L.mf.exchange_ghosts(cur, nb, L.stride, kd, 1);
+                SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
+                                               own_dinv ? nullptr : L.dinv.data(), L.stride, f1.data(), f2.data()));
+              }
             std::swap(cur, old);
           }
         if (cur != x.data()) // odd number of steps: result sits in the tmp buffer
-          SPIRK_CHECK(spirk_vec_copy(dev->ctx(), x.data(), cur, L.n * nb));
+          SPIRK_CHECK(spirk_vec_copy(dev->ctx(), x.data(), cur, (long long)(nb - 1) * L.stride + L.n));
       }
 
       static bool fuse_first_iterations()
@@ -238,7 +253,7 @@ namespace spirk_host
       {
         MGLevel &L = levels[0];
         if (coarse_exact)
-          SPIRK_CHECK(spirk_dense_matvec(dev->ctx(), (int)L.n, nb, L.solution.data(), L.defect.data(), L.n, coarse_inverse.data(),
+          SPIRK_CHECK(spirk_dense_matvec(dev->ctx(), (int)L.n, nb, L.solution.data(), L.defect.data(), L.stride, coarse_inverse.data(),
                                          L.n * L.n));
         else
           smooth_zero_start(0, L.solution, L.defect); // MGCoarseGridApplyPreconditioner on the smoother
@@ -255,15 +270,41 @@ namespace spirk_host
         MGLevel           &L  = levels[l];
         MGLevel           &Lc = levels[l - 1];
         const spirk_opdesc op = opdesc(l);
+        const int kd = L.level.degree;
         smooth_zero_start(l, L.solution, L.defect);
-        SPIRK_CHECK(spirk_op_residual(dev->ctx(), &L.level, &op, L.t.data(), L.defect.data(), L.solution.data(), L.n));
-        SPIRK_CHECK(spirk_mg_restrict(dev->ctx(), &L.level, nb, Lc.defect.data(), Lc.n, L.t.data(), L.n));
+        L.mf.exchange_ghosts_for_operator(L.solution);
+        SPIRK_CHECK(spirk_op_residual(dev->ctx(), &L.level, &op, L.t.data(), L.defect.data(), L.solution.data(), L.stride));
+        // restriction reads 2k fine planes below and one above the owned range; a replicated coarse level receives the planes
+        // of every slab (all-gather over the column communicator; its top plane is Dirichlet)
+        L.mf.exchange_ghosts(L.t, SPIRK_SLAB_PAD_LO(kd), SPIRK_SLAB_PAD_HI);
+        SPIRK_CHECK(spirk_mg_restrict(dev->ctx(), &L.level, nb, Lc.defect.data(), Lc.stride, L.t.data(), L.stride));
+        if (L.mf.partitioned() && !Lc.mf.partitioned())
+          gather_replicated(L, Lc, Lc.defect);
         level_v_step(l - 1);
-        SPIRK_CHECK(spirk_mg_prolongate_add(dev->ctx(), &L.level, nb, L.solution.data(), L.n, Lc.solution.data(), Lc.n));
+        if (Lc.mf.partitioned())
+          Lc.mf.exchange_ghosts(Lc.solution, 0, 1); // prolongation reads the coarse plane on top of the slab
+        SPIRK_CHECK(spirk_mg_prolongate_add(dev->ctx(), &L.level, nb, L.solution.data(), L.stride, Lc.solution.data(), Lc.stride));
         // post-smoothing: x += S (b - A x)
-        SPIRK_CHECK(spirk_op_residual(dev->ctx(), &L.level, &op, L.t.data(), L.defect.data(), L.solution.data(), L.n));
+        L.mf.exchange_ghosts_for_operator(L.solution);
+        SPIRK_CHECK(spirk_op_residual(dev->ctx(), &L.level, &op, L.t.data(), L.defect.data(), L.solution.data(), L.stride));
         smooth_zero_start(l, L.d, L.t);
         L.solution.add(1.0, L.d);
+      }
+
+      // The coarse level below a z-slab level is held in full by every rank of the column (agglomerated coarse levels:
+      // every rank repeats the small coarse-level work instead of idling, the analogue of create_sub_comm,
+      // preconditioner.h:287-339).  After the restriction every rank holds the coarse planes of its own slab: all-gather.
+      void gather_replicated(const MGLevel &L, const MGLevel &Lc, Vector &v)
+      {
+        const int       col_size = (L.level.slab >> 8) & 0xff, col_rank = L.level.slab & 0xff;
+        const int       n1c = Lc.mf.n1(), kd = Lc.level.degree;
+        const long long plane = (long long)n1c * n1c, count = (long long)kd * (Lc.level.n_cells_1d / col_size) * plane;
+        for (int b = 0; b < nb; ++b)
+          {
+            double *base = v.data() + b * v.stride();
+            SPIRK_CHECK(spirk_comm_allgather(dev->ctx(), L.mf.column_comm, base, base + col_rank * count, count));
+          }
+        SPIRK_CHECK(spirk_constraints_set_zero(dev->ctx(), &Lc.level, nb, v.data(), v.stride()));
       }
 
       bool same_descriptors(const std::vector<spirk_opdesc> &a) const
@@ -378,8 +419,9 @@ namespace spirk_host
       for (unsigned int level = min_level; level <= max_level; ++level)
         {
           auto &L = c.levels[level];
-          L.level = mg_operators[level]->get_matrix_free().level;
-          L.n     = mg_operators[level]->get_matrix_free().n_dofs();
+          L.mf    = mg_operators[level]->get_matrix_free();
+          L.level = L.mf.level;
+          L.n     = L.mf.n_dofs();
           mg_operators[level]->compute_inverse_diagonal(L.dinv);
           const spirk_opdesc d = mg_operators[level]->descriptor();
           if (d.kind == SPIRK_OP_REAL)
@@ -424,13 +466,17 @@ namespace spirk_host
       op->initialize_block_vector(sol);
       // set_initial_guess: (global index % 11) minus its mean, block by block
       {
+        // over the WHOLE level; a z-slab holds the entries [first, first + n) of it
+        const long long n1 = L.mf.n1(), plane = (L.level.dim == 3) ? n1 * n1 : n1;
+        const long long n_global = plane * n1;
+        const int       col_size = (L.level.slab >> 8) & 0xff, col_rank = L.level.slab & 0xff;
+        const long long first    = (col_size > 1) ? (long long)L.level.degree * (L.level.n_cells_1d * col_rank / col_size) * plane : 0;
+        const long long rem      = n_global % 11;
+        const double    sum      = 55.0 * (double)(n_global / 11) + 0.5 * (double)(rem * (rem - 1));
+        const double    mean     = sum / (double)n_global;
         std::vector<double> g((size_t)L.n);
-        double              sum = 0;
         for (long long i = 0; i < L.n; ++i)
-          g[i] = (double)(i % 11), sum += g[i];
-        const double mean = sum / (double)L.n;
-        for (auto &v : g)
-          v -= mean;
+          g[i] = (double)((first + i) % 11) - mean;
         for (int b = 0; b < c.nb; ++b)
           rhs.block(b).copy_from_host(g.data());
       }
@@ -527,7 +573,7 @@ namespace spirk_host
       for (unsigned int l = 0; l < c0.levels.size(); ++l)
         {
           auto &L = core.levels[l];
-          L.level = c0.levels[l].level, L.n = c0.levels[l].n;
+          L.level = c0.levels[l].level, L.n = c0.levels[l].n, L.mf = c0.levels[l].mf;
           L.dinv.reinit(*core.dev, L.n, nb, true);
           L.theta.resize(nb), L.delta.resize(nb);
           for (int b = 0; b < nb; ++b)

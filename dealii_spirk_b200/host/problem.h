@@ -114,6 +114,14 @@ namespace spirk_host
       }
     };
 
+    // the column (space) part of the reference's rectangular process grid (main.cc:3660-3698): this process holds z-slab
+    // `rank` of `size` of every partitioned level
+    struct ColumnComm
+    {
+      spirk_comm *comm = nullptr;
+      int         rank = 0, size = 1;
+    };
+
     class ProblemBase
     {
     public:
@@ -138,7 +146,9 @@ namespace spirk_host
       double              time            = 0.0;
       unsigned int        timestep_number = 0;
       double              time_step_size  = 0.0;
-      long long           n_dofs          = 0;
+      long long           n_dofs          = 0; // of the whole mesh
+      long long           n_dofs_owned    = 0; // held by this process (a z-slab when the mesh is partitioned)
+      long long           first_owned     = 0; // lexicographic index of the first owned DoF
       bool                compute_errors  = true;
     };
 
@@ -147,10 +157,11 @@ namespace spirk_host
     {
     public:
       Problem(const Parameters &params, Device &device, const TimeIntegrationSchemes::RowComm comm_row, ConvergenceTable &table,
-              std::ostream *pcout)
+              std::ostream *pcout, const ColumnComm comm_column = ColumnComm())
         : params(params)
         , device(device)
         , comm_row(comm_row)
+        , comm_column(comm_column)
         , table(table)
         , pcout(pcout)
       {}
@@ -164,8 +175,28 @@ namespace spirk_host
         const std::string &scheme = params.time_integration_scheme;
         const unsigned int r = params.n_refinements, k = params.fe_degree, q = params.irk_stages;
 
-        mass_laplace_operator = std::make_unique<MassLaplaceOperatorMatrixFree<dim>>(device, k, r);
-        n_dofs                = mass_laplace_operator->m();
+        // Spatial partition (the reference's triangulation on comm_column, main.cc:3027, 3478): level l is split into z-slabs
+        // when the plane-streaming cell operator covers it and every slab keeps an even number of cell layers (so that the
+        // next coarser level splits at the same planes); coarser levels are held in full by every rank of the column.
+        const int  C = comm_column.size;
+        const auto partitioned = [&](unsigned int l) { return C > 1 && dim == 3 && k == 4 && (1u << l) >= 8 && (1u << l) % (2 * C) == 0; };
+        if (C > 1 && !partitioned(r))
+          throw Error("spatial partition: needs 3-D, FEDegree 4 and 2^NRefinements a multiple of twice the number of slabs (>= 8 cells)");
+        if (C > 1 && (scheme.rfind("complex", 0) == 0 || scheme == "irk_batched" || comm_row.size * 1u != ((scheme == "spirk") ? q : 1u)))
+          throw Error("spatial partition is built for one stage per row rank (spirk with IRKStages row ranks, irk / ost with one)");
+        const auto make_level_operator = [&](unsigned int l) {
+          if (partitioned(l))
+            return std::make_shared<MassLaplaceOperatorMatrixFree<dim>>(device, k, l, comm_column.comm, comm_column.rank, C,
+                                                                        /*coarse_replicated=*/l == 0 || !partitioned(l - 1));
+          return std::make_shared<MassLaplaceOperatorMatrixFree<dim>>(device, k, l);
+        };
+        mass_laplace_operator = make_level_operator(r);
+        n_dofs_owned          = mass_laplace_operator->m();
+        {
+          const long long n1 = (long long)k * (1u << r) + 1;
+          n_dofs             = (dim == 3) ? n1 * n1 * n1 : n1 * n1;
+          first_owned        = (C > 1) ? (long long)k * ((1u << r) * comm_column.rank / C) * n1 * n1 : 0;
+        }
         if (pcout)
           *pcout << std::endl
                  << "===========================================" << std::endl
@@ -177,10 +208,10 @@ namespace spirk_host
         table.add_value("fe_degree", k);
         table.add_value("n_dofs", (double)n_dofs);
         table.add_value("n_stages", q);
-        table.add_value("n_procs", comm_row.size);
-        table.add_value("n_procs_global", comm_row.size);
+        table.add_value("n_procs", comm_row.size * C);
+        table.add_value("n_procs_global", comm_row.size * C);
         table.add_value("n_procs_row", comm_row.size);
-        table.add_value("n_procs_column", 1);
+        table.add_value("n_procs_column", C);
 
         const bool is_complex = scheme.rfind("complex", 0) == 0;
         if (is_complex)
@@ -191,7 +222,7 @@ namespace spirk_host
         typename PreconditionerGMG<dim, MassLaplaceOperator>::LevelOperators mg_operators;
         for (unsigned int l = 0; l <= r; ++l)
           {
-            auto lop = std::make_shared<MassLaplaceOperatorMatrixFree<dim>>(device, k, l);
+            auto lop = make_level_operator(l);
             mass_laplace_operator->attach(*lop);
             mg_operators.push_back(lop);
           }
@@ -325,7 +356,23 @@ namespace spirk_host
         // VTU output (DoOutputParaview) is out of scope; the error norms are the reference's own check
         double l2 = 0, linf = 0;
         if (compute_errors)
-          SPIRK_CHECK(spirk_problem_error_norms(device.ctx(), &level(), solution.data(), time, &l2, &linf));
+          {
+            // the cells of this process's slab (they read one ghost plane above), then sum / max over the column
+            mass_laplace_operator->get_matrix_free().exchange_ghosts(solution, 0, 1);
+            SPIRK_CHECK(spirk_problem_error_norms_partial(device.ctx(), &level(), solution.data(), time, &l2, &linf));
+            if (comm_column.size > 1)
+              {
+                Vector t;
+                t.reinit(device, 2, 1, true);
+                double v[2] = {l2, linf};
+                t.copy_from_host(v);
+                SPIRK_CHECK(spirk_comm_allreduce_sum(device.ctx(), comm_column.comm, t.data(), 1));
+                SPIRK_CHECK(spirk_comm_allreduce_max(device.ctx(), comm_column.comm, t.data() + 1, 1));
+                t.copy_to_host(v);
+                l2 = v[0], linf = v[1];
+              }
+            l2 = std::sqrt(l2);
+          }
         step_time.push_back(time);
         error_L2.push_back(l2);
         error_Linf.push_back(linf);
@@ -337,10 +384,11 @@ namespace spirk_host
       const Parameters                      params;
       Device                               &device;
       const TimeIntegrationSchemes::RowComm comm_row;
+      const ColumnComm                      comm_column;
       ConvergenceTable                     &table;
       std::ostream                         *pcout;
 
-      std::unique_ptr<MassLaplaceOperatorMatrixFree<dim>>   mass_laplace_operator;
+      std::shared_ptr<MassLaplaceOperatorMatrixFree<dim>>   mass_laplace_operator;
       std::unique_ptr<ComplexMassLaplaceOperator>           complex_mass_laplace_operator;
       std::unique_ptr<PreconditionerBase<VectorType>>       preconditioner;
       std::shared_ptr<PreconditionerBase<BlockVectorType>>  preconditioner_batch;

@@ -276,7 +276,10 @@ namespace spirk_host
       double norm = 0;
       if (vv.reduction_comm())
         spirk_ctx_set_reduction_comm(vv.ctx(), vv.reduction_comm());
-      const int st = spirk_gmres_mgs(vv.ctx(), vv.data(), ptrs.data(), (int)dim, vv.size(), h, &norm);
+      const int st = vv.contiguous() ?
+                       spirk_gmres_mgs(vv.ctx(), vv.data(), ptrs.data(), (int)dim, vv.size(), h, &norm) :
+                       spirk_gmres_mgs_strided(vv.ctx(), vv.data(), ptrs.data(), (int)dim, vv.block_size(), (int)vv.n_blocks(), vv.stride(),
+                                               h, &norm);
       if (vv.reduction_comm())
         spirk_ctx_set_reduction_comm(vv.ctx(), nullptr);
       check(st, "spirk_gmres_mgs");

@@ -34,9 +34,14 @@ namespace spirk_host
     {
       spirk_comm  *comm = nullptr;
       unsigned int rank = 0, size = 1;
+      // what the inner products of the stage-coupled vectors are summed over (ReshapedVector, main.cc:237-264): the row
+      // communicator, or row x column when the mesh is partitioned as well (nullptr: `comm`)
+      spirk_comm *reduce = nullptr;
+      spirk_comm *reduction_comm() const { return reduce ? reduce : comm; }
       RowComm()        = default;
-      explicit RowComm(spirk_comm *c)
+      explicit RowComm(spirk_comm *c, spirk_comm *row_x_column = nullptr)
         : comm(c)
+        , reduce(row_x_column)
       {
         if (c)
           {
@@ -119,7 +124,7 @@ namespace spirk_host
       for (unsigned int i = 0; i < nrows; ++i)
         for (unsigned int j = 0; j < T.n(); ++j)
           rows[(size_t)i * T.n() + j] = T(row0 + i, j);
-      SPIRK_CHECK(spirk_mix(dst.ctx(), nrows, T.n(), dst.data(), dst.block_size(), src.data(), src.block_size(), dst.block_size(),
+      SPIRK_CHECK(spirk_mix(dst.ctx(), nrows, T.n(), dst.data(), dst.stride(), src.data(), src.stride(), dst.block_size(),
                             rows.data(), add ? 1 : 0, cutoff));
     }
 
@@ -329,7 +334,7 @@ namespace spirk_host
         BlockVectorType system_rhs, system_solution, g;
         VectorType      tmp;
         system_rhs.reinit(dev, N, m_local), system_solution.reinit(dev, N, m_local), g.reinit(dev, N, m_local, true);
-        system_rhs.set_reduction_comm(row.comm), system_solution.set_reduction_comm(row.comm);
+        system_rhs.set_reduction_comm(row.reduction_comm()), system_solution.set_reduction_comm(row.reduction_comm());
         tmp.reinit(solution, true);
 
         // right-hand side g_i = f(t + (c_i - 1) tau) - K u_n, then rhs = (A_inv (x) I) g   (main.cc:867-891, 1343-1349)
@@ -400,7 +405,7 @@ namespace spirk_host
             w[i] = time_step * b_vec[s0 + i];
           if (row.size > 1 && row.rank != 0)
             solution = 0.0;
-          SPIRK_CHECK(spirk_mix(dev.ctx(), 1, m_local, solution.data(), N, system_solution.data(), N, N, w.data(), 1, 0.0));
+          SPIRK_CHECK(spirk_mix(dev.ctx(), 1, m_local, solution.data(), N, system_solution.data(), system_solution.stride(), N, w.data(), 1, 0.0));
           row.all_reduce_sum(solution);
         }
         const double t_end = now_ns(solution, true);
@@ -433,7 +438,8 @@ namespace spirk_host
             // ONE kernel contracts over all stages reading the remote blocks over NVLink (the reference's MPI-3
             // shared-memory variant, main.cc:1506-1533); no gathered copy is written
             const long long n = src.block_size();
-            SPIRK_CHECK(spirk_vec_copy(src.ctx(), spirk_comm_xbuf_local(xbuf), src.data(), n * m_local));
+            for (unsigned int i = 0; i < m_local; ++i)
+              SPIRK_CHECK(spirk_vec_copy(src.ctx(), spirk_comm_xbuf_local(xbuf) + i * n, src.data() + i * src.stride(), n));
             if (xbuf_a2a)
               {
                 // all-to-all: every rank contracts its chunk of every stage block for all outputs (full T)
@@ -441,7 +447,7 @@ namespace spirk_host
                 for (unsigned int i = 0; i < Tm.m(); ++i)
                   for (unsigned int j = 0; j < Tm.n(); ++j)
                     full[(size_t)i * Tm.n() + j] = Tm(i, j);
-                SPIRK_CHECK(spirk_mix_peer_a2a(src.ctx(), row.comm, xbuf, (int)m_local, dst.data(), dst.block_size(), n, full.data(),
+                SPIRK_CHECK(spirk_mix_peer_a2a(src.ctx(), row.comm, xbuf, (int)m_local, dst.data(), dst.stride(), n, full.data(),
                                                add ? 1 : 0, cutoff));
                 return;
               }
@@ -449,12 +455,15 @@ namespace spirk_host
             for (unsigned int i = 0; i < m_local; ++i)
               for (unsigned int j = 0; j < Tm.n(); ++j)
                 rows[(size_t)i * Tm.n() + j] = Tm(s0 + i, j);
-            SPIRK_CHECK(spirk_mix_peer(src.ctx(), row.comm, xbuf, (int)m_local, (int)m_local, dst.data(), dst.block_size(), n,
+            SPIRK_CHECK(spirk_mix_peer(src.ctx(), row.comm, xbuf, (int)m_local, (int)m_local, dst.data(), dst.stride(), n,
                                        rows.data(), add ? 1 : 0, cutoff));
             return;
           }
-        gathered.reinit(src.device(), src.block_size(), n_stages, true);
-        row.all_gather(gathered, src);
+        // (contiguous staging: the all-gather needs the stage blocks of a rank back to back)
+        gather_send.view_or_pack(src);
+        gathered_flat.reinit(src.device(), src.block_size() * n_stages + 1, 1, true);
+        SPIRK_CHECK(spirk_comm_allgather(src.ctx(), row.comm, gathered_flat.data(), gather_send.data(), src.block_size() * m_local));
+        gathered.view(src.device(), gathered_flat.data(), src.block_size(), n_stages);
         mix_rows(dst, gathered, Tm, s0, m_local, add, cutoff);
       }
 
@@ -507,7 +516,8 @@ namespace spirk_host
                   for (unsigned int j = 0; j < p.n_stages; ++j)
                     d.coupling[i * p.n_stages + j] = p.A_inv(i, j);
                 }
-              SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &d, dst.data(), src.data(), src.block_size()));
+              mf.exchange_ghosts_for_operator(src);
+              SPIRK_CHECK(spirk_op_apply(src.ctx(), &mf.level, &d, dst.data(), src.data(), src.stride()));
             }
           else
             {
@@ -516,8 +526,10 @@ namespace spirk_host
               std::vector<double> one(p.m_local, 1.0), tau(p.m_local, p.time_step);
               p.temp.reinit(src, true);
               p.perform_basis_change(p.temp, src, p.A_inv, false, 0.0);
+              mf.exchange_ghosts_for_operator(src);
+              mf.exchange_ghosts_for_operator(p.temp);
               SPIRK_CHECK(spirk_op_apply_km(src.ctx(), &mf.level, (int)p.m_local, dst.data(), src.data(), p.temp.data(),
-                                            src.block_size(), tau.data(), one.data()));
+                                            src.stride(), tau.data(), one.data()));
             }
           p.time_system_vmult += now_ns(src) - t0;
         }
@@ -623,7 +635,27 @@ namespace spirk_host
       mutable std::vector<unsigned int> n_inner;
       mutable std::vector<std::unique_ptr<const PreconditionerBase<VectorType>>> preconditioners;
       mutable std::unique_ptr<StageBatchedGMG<dim>> stage_batch;
-      mutable Vector temp, tmp_vectors, gathered;
+      mutable Vector temp, tmp_vectors, gathered, gathered_flat;
+      // the local stage blocks back to back (a view of the vector itself when it is contiguous)
+      struct Packed
+      {
+        Vector        owned;
+        const double *ptr = nullptr;
+        const double *data() const { return ptr; }
+        void          view_or_pack(const Vector &v)
+        {
+          if (v.contiguous())
+            {
+              ptr = v.data();
+              return;
+            }
+          owned.reinit(v.device(), v.block_size() * v.n_blocks() + 1, 1, true);
+          for (unsigned int b = 0; b < v.n_blocks(); ++b)
+            SPIRK_CHECK(spirk_vec_copy(v.ctx(), owned.data() + b * v.block_size(), v.data() + b * v.stride(), v.block_size()));
+          ptr = owned.data();
+        }
+      };
+      mutable Packed gather_send;
     };
 
     // the reference's two class names

@@ -75,9 +75,26 @@ namespace spirk_host
     }
     long long bytes_allocated = 0;
 
+    // z-slab levels (spatial partition): every block of `n_owned` entries is allocated with `lo` entries of ghost planes
+    // below and `hi` above its owned range (SPIRK_SLAB_PAD_LO / _HI planes); registered by the level operators
+    struct Padding
+    {
+      long long lo = 0, hi = 0;
+    };
+    void register_padding(long long n_owned, long long lo, long long hi) { paddings_[n_owned] = Padding{lo, hi}; }
+    Padding padding_for(long long n) const
+    {
+      auto it = paddings_.find(n);
+      return it == paddings_.end() ? Padding{} : it->second;
+    }
+    // the column (space) communicator of this process: inner products of vectors on z-slab levels are summed over it
+    spirk_comm *column_comm = nullptr;
+    spirk_comm *column_comm_for(long long n) const { return paddings_.count(n) ? column_comm : nullptr; }
+
   private:
     spirk_ctx                               *ctx_ = nullptr;
     std::map<long long, std::vector<double *>> pool_;
+    std::map<long long, Padding>               paddings_;
   };
 
   class Vector
@@ -102,23 +119,29 @@ namespace spirk_host
     void clear()
     {
       views_.clear();
-      if (owns_ && data_)
-        dev_->release(data_, size_);
-      data_ = nullptr, size_ = 0, owns_ = false;
+      if (owns_ && raw_)
+        dev_->release(raw_, alloc_);
+      data_ = raw_ = nullptr, size_ = alloc_ = 0, owns_ = false;
     }
 
-    // allocate n_blocks contiguous blocks of block_size entries (zeroed unless omitted)
+    // allocate n_blocks blocks of block_size entries (zeroed unless omitted); contiguous unless the device has ghost-plane
+    // padding registered for this block size (z-slab levels): then block b starts at data() + b * stride()
     void reinit(Device &dev, long long block_size, int n_blocks = 1, bool omit_zeroing_entries = false)
     {
-      const long long n = block_size * n_blocks;
-      if (!(owns_ && dev_ == &dev && size_ == n))
+      const long long      n   = block_size * n_blocks;
+      const Device::Padding pad = dev.padding_for(block_size);
+      const long long      st  = block_size + pad.lo + pad.hi;
+      if (!(owns_ && dev_ == &dev && size_ == n && stride_ == st))
         {
           clear();
-          dev_  = &dev;
-          data_ = dev.acquire(n);
+          dev_   = &dev;
+          alloc_ = st * n_blocks;
+          raw_   = dev.acquire(alloc_);
+          data_  = raw_ + pad.lo;
           size_ = n, owns_ = true;
         }
-      n_blocks_ = n_blocks, block_size_ = block_size;
+      n_blocks_ = n_blocks, block_size_ = block_size, stride_ = st;
+      column_comm_ = dev.column_comm_for(block_size);
       views_.clear();
       if (!omit_zeroing_entries)
         *this = 0.0;
@@ -128,17 +151,22 @@ namespace spirk_host
       reinit(*other.dev_, other.block_size_, other.n_blocks_, omit_zeroing_entries);
       reduction_comm_ = other.reduction_comm_;
     }
-    // non-owning view
-    void view(Device &dev, double *data, long long block_size, int n_blocks = 1)
+    // non-owning view (blocks at `stride`, 0 = contiguous)
+    void view(Device &dev, double *data, long long block_size, int n_blocks = 1, long long stride = 0)
     {
       clear();
       dev_ = &dev, data_ = data, size_ = block_size * n_blocks, owns_ = false;
-      n_blocks_ = n_blocks, block_size_ = block_size;
+      n_blocks_ = n_blocks, block_size_ = block_size, stride_ = stride ? stride : block_size;
+      column_comm_ = dev.column_comm_for(block_size);
     }
+
+    // entries from data() that pointwise operations run over: contiguous vectors as they are; padded block vectors
+    // including the ghost planes between the blocks (finite values, never read as results)
+    long long span() const { return (long long)(n_blocks_ - 1) * stride_ + block_size_; }
 
     Vector &operator=(const double s)
     {
-      SPIRK_CHECK(spirk_vec_set(ctx(), data_, size_, s));
+      SPIRK_CHECK(spirk_vec_set(ctx(), data_, span(), s));
       return *this;
     }
     Vector &operator=(const Vector &V)
@@ -147,21 +175,38 @@ namespace spirk_host
         return *this;
       if (size_ != V.size_ || !data_)
         reinit(V, true);
-      SPIRK_CHECK(spirk_vec_copy(ctx(), data_, V.data_, size_));
+      if (stride_ == V.stride_)
+        SPIRK_CHECK(spirk_vec_copy(ctx(), data_, V.data_, span()));
+      else
+        for (int b = 0; b < n_blocks_; ++b)
+          SPIRK_CHECK(spirk_vec_copy(ctx(), data_ + b * stride_, V.data_ + b * V.stride_, block_size_));
       return *this;
     }
     void copy_locally_owned_data_from(const Vector &V) { *this = V; }
 
-    void add(double a, const Vector &V) { SPIRK_CHECK(spirk_vec_axpy(ctx(), data_, a, V.data_, size_)); }
+    void add(double a, const Vector &V)
+    {
+      same_layout(V);
+      SPIRK_CHECK(spirk_vec_axpy(ctx(), data_, a, V.data_, span()));
+    }
     void add(double a, const Vector &V, double b, const Vector &W)
     {
-      SPIRK_CHECK(spirk_vec_add2(ctx(), data_, a, V.data_, b, W.data_, size_));
+      same_layout(V), same_layout(W);
+      SPIRK_CHECK(spirk_vec_add2(ctx(), data_, a, V.data_, b, W.data_, span()));
     }
-    void sadd(double s, double a, const Vector &V) { SPIRK_CHECK(spirk_vec_sadd(ctx(), data_, s, a, V.data_, size_)); }
-    void equ(double a, const Vector &V) { SPIRK_CHECK(spirk_vec_equ(ctx(), data_, a, V.data_, size_)); }
+    void sadd(double s, double a, const Vector &V)
+    {
+      same_layout(V);
+      SPIRK_CHECK(spirk_vec_sadd(ctx(), data_, s, a, V.data_, span()));
+    }
+    void equ(double a, const Vector &V)
+    {
+      same_layout(V);
+      SPIRK_CHECK(spirk_vec_equ(ctx(), data_, a, V.data_, span()));
+    }
     Vector &operator*=(double a)
     {
-      SPIRK_CHECK(spirk_vec_scale(ctx(), data_, size_, a));
+      SPIRK_CHECK(spirk_vec_scale(ctx(), data_, span(), a));
       return *this;
     }
     Vector &operator+=(const Vector &V)
@@ -180,7 +225,11 @@ namespace spirk_host
     {
       double     r = 0;
       CommGuard g(*this);
-      SPIRK_CHECK(spirk_vec_dot(ctx(), data_, V.data_, size_, &r));
+      same_layout(V);
+      if (contiguous())
+        SPIRK_CHECK(spirk_vec_dot(ctx(), data_, V.data_, size_, &r));
+      else
+        SPIRK_CHECK(spirk_vec_dot_strided(ctx(), data_, V.data_, block_size_, n_blocks_, stride_, &r));
       return r;
     }
     double norm_sqr() const { return (*this) * (*this); }
@@ -189,13 +238,20 @@ namespace spirk_host
     {
       double     r = 0;
       CommGuard g(*this);
-      SPIRK_CHECK(spirk_vec_add_and_dot(ctx(), data_, a, V.data_, W.data_, size_, &r));
+      same_layout(V), same_layout(W);
+      if (contiguous())
+        SPIRK_CHECK(spirk_vec_add_and_dot(ctx(), data_, a, V.data_, W.data_, size_, &r));
+      else
+        SPIRK_CHECK(spirk_vec_add_and_dot_strided(ctx(), data_, a, V.data_, W.data_, block_size_, n_blocks_, stride_, &r));
       return r;
     }
     double mean_value() const
     {
       double r = 0;
-      SPIRK_CHECK(spirk_vec_sum(ctx(), data_, size_, &r));
+      if (contiguous())
+        SPIRK_CHECK(spirk_vec_sum(ctx(), data_, size_, &r));
+      else
+        SPIRK_CHECK(spirk_vec_sum_strided(ctx(), data_, block_size_, n_blocks_, stride_, &r));
       return r / (double)size_;
     }
     bool all_zero() const { return norm_sqr() == 0.0; }
@@ -212,6 +268,8 @@ namespace spirk_host
     // block interface (BlockVector)
     unsigned int n_blocks() const { return n_blocks_; }
     long long    block_size() const { return block_size_; }
+    long long    stride() const { return stride_; }              // distance between the first entries of consecutive blocks
+    bool         contiguous() const { return n_blocks_ == 1 || stride_ == block_size_; }
     Vector      &block(unsigned int i)
     {
       make_views();
@@ -228,11 +286,28 @@ namespace spirk_host
     void update_ghost_values() const {}
     void zero_out_ghost_values() const {}
 
+    // the communicator inner products are summed over: an explicit one (ReshapedVector: the stage communicator, or stage x
+    // space), else the column communicator of a z-slab level, else none
     void set_reduction_comm(spirk_comm *c) { reduction_comm_ = c; }
-    spirk_comm *reduction_comm() const { return reduction_comm_; }
+    spirk_comm *reduction_comm() const { return effective_comm(); }
+    spirk_comm *effective_comm() const { return reduction_comm_ ? reduction_comm_ : column_comm_; }
 
-    void copy_to_host(double *host) const { SPIRK_CHECK(spirk_copy_d2h(ctx(), host, data_, (size_t)size_)); }
-    void copy_from_host(const double *host) { SPIRK_CHECK(spirk_copy_h2d(ctx(), data_, host, (size_t)size_)); }
+    void copy_to_host(double *host) const
+    {
+      if (contiguous())
+        SPIRK_CHECK(spirk_copy_d2h(ctx(), host, data_, (size_t)size_));
+      else
+        for (int b = 0; b < n_blocks_; ++b)
+          SPIRK_CHECK(spirk_copy_d2h(ctx(), host + b * block_size_, data_ + b * stride_, (size_t)block_size_));
+    }
+    void copy_from_host(const double *host)
+    {
+      if (contiguous())
+        SPIRK_CHECK(spirk_copy_h2d(ctx(), data_, host, (size_t)size_));
+      else
+        for (int b = 0; b < n_blocks_; ++b)
+          SPIRK_CHECK(spirk_copy_h2d(ctx(), data_ + b * stride_, host + b * block_size_, (size_t)block_size_));
+    }
     std::vector<double> to_host() const
     {
       std::vector<double> h((size_t)size_);
@@ -243,7 +318,9 @@ namespace spirk_host
     void swap(Vector &o) noexcept
     {
       std::swap(dev_, o.dev_), std::swap(data_, o.data_), std::swap(size_, o.size_), std::swap(owns_, o.owns_);
+      std::swap(raw_, o.raw_), std::swap(alloc_, o.alloc_), std::swap(stride_, o.stride_);
       std::swap(n_blocks_, o.n_blocks_), std::swap(block_size_, o.block_size_), std::swap(reduction_comm_, o.reduction_comm_);
+      std::swap(column_comm_, o.column_comm_);
       views_.clear(), o.views_.clear();
     }
 
@@ -254,12 +331,12 @@ namespace spirk_host
       explicit CommGuard(const Vector &v)
         : v(v)
       {
-        if (v.reduction_comm_)
-          spirk_ctx_set_reduction_comm(v.ctx(), v.reduction_comm_);
+        if (v.effective_comm())
+          spirk_ctx_set_reduction_comm(v.ctx(), v.effective_comm());
       }
       ~CommGuard()
       {
-        if (v.reduction_comm_)
+        if (v.effective_comm())
           spirk_ctx_set_reduction_comm(v.ctx(), nullptr);
       }
     };
@@ -271,17 +348,23 @@ namespace spirk_host
       for (int b = 0; b < n_blocks_; ++b)
         {
           views_.emplace_back(new Vector());
-          views_.back()->view(*dev_, data_ + b * block_size_, block_size_, 1);
+          views_.back()->view(*dev_, data_ + b * stride_, block_size_, 1);
+          views_.back()->column_comm_ = column_comm_; // (not the row communicator: a stage block is local to its stage)
         }
+    }
+    void same_layout(const Vector &V) const
+    {
+      if (V.size_ != size_ || (n_blocks_ > 1 && V.stride_ != stride_))
+        throw Error("vector operation on vectors of different size / block layout");
     }
 
     Device    *dev_  = nullptr;
-    double    *data_ = nullptr;
-    long long  size_ = 0;
+    double    *data_ = nullptr, *raw_ = nullptr; // first owned entry; start of the allocation (ghost planes below)
+    long long  size_ = 0, alloc_ = 0, stride_ = 0;
     bool       owns_ = false;
     int        n_blocks_ = 1;
     long long  block_size_ = 0;
-    spirk_comm *reduction_comm_ = nullptr;
+    spirk_comm *reduction_comm_ = nullptr, *column_comm_ = nullptr;
     std::vector<std::unique_ptr<Vector>> views_;
   };
 

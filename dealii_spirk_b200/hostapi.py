@@ -119,7 +119,9 @@ class Run:
         return buf[:n.value].copy()
 
     def solution(self):
-        out = np.empty(int(self.scalar("n_dofs")))
+        """the solution entries this process owns: all of them, or (spatial partition) the z-slab starting at the lexicographic
+        index scalar("first_owned")"""
+        out = np.empty(int(self.scalar("n_dofs_owned")))
         self._call("get_solution", out.ctypes.data_as(C.c_void_p))
         return out
 

@@ -49,8 +49,19 @@ typedef struct
   int dim;        /* 2 or 3 */
   int degree;     /* k = 1..6 */
   int n_cells_1d; /* 2^r */
-  int reserved;
+  int slab;       /* 0: the whole mesh; else SPIRK_SLAB(rank, size[, coarse_replicated]): z-slab `rank` of `size` (3-D) */
 } spirk_level;
+/* Spatial partition (the reference's column communicator, main.cc:3027, 3478, 3660-3698): the cell layers are split into
+ * `size` equal z-slabs, n_cells_1d % size == 0.  A slab owns the node planes [k L_lo, k L_hi) (+ the top plane of the
+ * domain for the last slab); its vectors are the owned planes, contiguous, and every vector pointer handed to the library
+ * points at the first owned entry with SPIRK_SLAB_PAD_LO(k) ghost planes allocated below and SPIRK_SLAB_PAD_HI above
+ * (a plane = (k n_cells_1d + 1)^2 doubles; blocks of a block vector each carry their own pads inside `stride`).
+ * spirk_halo_exchange fills the ghost planes from the neighbouring slabs.  spirk_level_n_dofs = owned entries.
+ * coarse_replicated: the next coarser level is held in full by every rank of the column (agglomerated coarse levels,
+ * the analogue of create_sub_comm, preconditioner.h:287-339): the transfers address it by global plane. */
+#define SPIRK_SLAB(rank, size, coarse_replicated) ((rank) | ((size) << 8) | ((coarse_replicated) ? (1 << 16) : 0))
+#define SPIRK_SLAB_PAD_LO(k) (2 * (k)) /* restriction reads 2k fine planes below the owned range, the operator k */
+#define SPIRK_SLAB_PAD_HI 1
 
 /* Operator descriptor.  dst_i = laplace[i] * K src_i + M * sum_j coupling[i*nb+j] src_j on
  * unconstrained DoFs, dst_i = src_i on Dirichlet DoFs.
@@ -179,6 +190,15 @@ int spirk_vec_dot(spirk_ctx *ctx, const double *x, const double *y, long long n,
 int spirk_vec_add_and_dot(spirk_ctx *ctx, double *v, double a, const double *V, const double *W,
                           long long n, double *host_result);
 int spirk_vec_sum(spirk_ctx *ctx, const double *x, long long n, double *host_result);
+/* the reductions over block vectors whose nb blocks of n entries sit at `stride` > n (z-slab vectors: ghost planes between
+ * the blocks are skipped) */
+int spirk_vec_dot_strided(spirk_ctx *ctx, const double *x, const double *y, long long n, int nb, long long stride,
+                          double *host_result);
+int spirk_vec_sum_strided(spirk_ctx *ctx, const double *x, long long n, int nb, long long stride, double *host_result);
+int spirk_vec_add_and_dot_strided(spirk_ctx *ctx, double *v, double a, const double *V, const double *W, long long n, int nb,
+                                  long long stride, double *host_result);
+int spirk_gmres_mgs_strided(spirk_ctx *ctx, double *vv, const double *const *host_basis, int dim, long long n, int nb,
+                            long long stride, double *host_h, double *host_norm);
 /* modified Gram-Schmidt sweep of SolverGMRES in one call:
  *   h[0] = vv.q0; h[i] = (vv -= h[i-1] q_{i-1}).q_i; norm = sqrt((vv -= h[dim-1] q_{dim-1}).vv)
  * host_basis[i] is the DEVICE pointer of basis vector i; h (dim) and norm are HOST outputs */
@@ -199,6 +219,10 @@ int spirk_problem_interpolate_solution(spirk_ctx *ctx, const spirk_level *lvl, d
 /* L2 and Linf error against the analytical solution with QGauss(k+2) (main.cc:3436-3469) */
 int spirk_problem_error_norms(spirk_ctx *ctx, const spirk_level *lvl, const double *u, double t,
                               double *host_l2, double *host_linf);
+/* the same over the cells of this level only (a z-slab: its cells; u needs one ghost plane above): the SQUARE of the L2
+ * norm and the maximum, to be summed / maximised over the column communicator by the caller */
+int spirk_problem_error_norms_partial(spirk_ctx *ctx, const spirk_level *lvl, const double *u, double t,
+                                      double *host_l2_squared, double *host_linf);
 /* AffineConstraints::set_zero / distribute for homogeneous Dirichlet (main.cc:3307, 3355) */
 int spirk_constraints_set_zero(spirk_ctx *ctx, const spirk_level *lvl, int nb, double *u,
                                long long stride);
@@ -210,6 +234,14 @@ int spirk_comm_destroy(spirk_comm *comm);
 int spirk_comm_rank(const spirk_comm *comm, int *rank, int *n_ranks);
 /* in-place sum over the communicator (MPI_Allreduce, main.cc:1421-1426, 241-263) */
 int spirk_comm_allreduce_sum(spirk_ctx *ctx, spirk_comm *comm, double *buf, long long n);
+/* MPI_Comm_split (main.cc:311, 334, 352; row / column communicators of the rectangular process grid, 3660-3698): collective */
+int spirk_comm_split(spirk_ctx *ctx, spirk_comm *comm, int color, int key, spirk_comm **out);
+int spirk_comm_allreduce_max(spirk_ctx *ctx, spirk_comm *comm, double *buf, long long n);
+/* Ghost planes of a z-slab vector (deal.II update_ghost_values inside cell_loop / the transfers, operator.h:301-306): fills
+ * the n_lo planes below and the n_hi planes above the owned range of each of the nb blocks from the neighbouring slabs over
+ * the column communicator (grouped ncclSend / ncclRecv over NVLink, stream ordered).  No-op for unpartitioned levels. */
+int spirk_halo_exchange(spirk_ctx *ctx, spirk_comm *column_comm, const spirk_level *lvl, int nb, double *vec, long long stride,
+                        int n_lo, int n_hi);
 /* recv[r*n .. r*n+n) = send of rank r (replaces the MPI_Sendrecv_replace ring, main.cc:1465-1483) */
 int spirk_comm_allgather(spirk_ctx *ctx, spirk_comm *comm, double *recv, const double *send,
                          long long n);

@@ -244,6 +244,8 @@ namespace
   {
     if (!l || (l->dim != 2 && l->dim != 3) || l->degree < 1 || l->degree > 6 || l->n_cells_1d < 1)
       return fail(SPIRK_ERR_INVALID, "bad level");
+    if (((l->slab >> 8) & 0xff) > 1)
+      return fail(SPIRK_ERR_UNSUPPORTED, "z-slab levels are not available on the CPU double");
     return SPIRK_OK;
   }
 
@@ -883,6 +885,61 @@ int spirk_vec_sum(spirk_ctx *, const double *x, long long n, double *r)
   *r = s;
   return SPIRK_OK;
 }
+// block vectors with a stride larger than the block length (z-slab vectors of the CUDA library): plain loops here
+int spirk_vec_dot_strided(spirk_ctx *ctx, const double *x, const double *y, long long n, int nb, long long stride, double *r)
+{
+  double s = 0;
+  for (int b = 0; b < nb; ++b)
+    {
+      double t = 0;
+      if (int e = spirk_vec_dot(ctx, x + b * stride, y + b * stride, n, &t))
+        return e;
+      s += t;
+    }
+  *r = s;
+  return SPIRK_OK;
+}
+int spirk_vec_sum_strided(spirk_ctx *ctx, const double *x, long long n, int nb, long long stride, double *r)
+{
+  double s = 0;
+  for (int b = 0; b < nb; ++b)
+    {
+      double t = 0;
+      if (int e = spirk_vec_sum(ctx, x + b * stride, n, &t))
+        return e;
+      s += t;
+    }
+  *r = s;
+  return SPIRK_OK;
+}
+int spirk_vec_add_and_dot_strided(spirk_ctx *ctx, double *v, double a, const double *V, const double *W, long long n, int nb,
+                                  long long stride, double *r)
+{
+  double s = 0;
+  for (int b = 0; b < nb; ++b)
+    {
+      double t = 0;
+      if (int e = spirk_vec_add_and_dot(ctx, v + b * stride, a, V + b * stride, (W == v ? v : W) + b * stride, n, &t))
+        return e;
+      s += t;
+    }
+  *r = s;
+  return SPIRK_OK;
+}
+int spirk_gmres_mgs_strided(spirk_ctx *ctx, double *vv, const double *const *basis, int dim, long long n, int nb, long long stride,
+                            double *h, double *norm)
+{
+  if (int e = spirk_vec_dot_strided(ctx, vv, basis[0], n, nb, stride, &h[0]))
+    return e;
+  for (int i = 1; i < dim; ++i)
+    if (int e = spirk_vec_add_and_dot_strided(ctx, vv, -h[i - 1], basis[i - 1], basis[i], n, nb, stride, &h[i]))
+      return e;
+  double s = 0;
+  if (int e = spirk_vec_add_and_dot_strided(ctx, vv, -h[dim - 1], basis[dim - 1], vv, n, nb, stride, &s))
+    return e;
+  *norm = std::sqrt(s);
+  return SPIRK_OK;
+}
 int spirk_gmres_mgs(spirk_ctx *ctx, double *vv, const double *const *basis, int dim, long long n, double *h, double *norm)
 {
   spirk_vec_dot(ctx, vv, basis[0], n, &h[0]);
@@ -971,6 +1028,15 @@ int spirk_problem_interpolate_solution(spirk_ctx *, const spirk_level *lvl, doub
   return SPIRK_OK;
 }
 
+int spirk_problem_error_norms(spirk_ctx *, const spirk_level *lvl, const double *u, double t, double *l2, double *linf);
+int spirk_problem_error_norms_partial(spirk_ctx *ctx, const spirk_level *lvl, const double *u, double t, double *l2sq, double *linf)
+{
+  double l2 = 0;
+  if (int e = spirk_problem_error_norms(ctx, lvl, u, t, &l2, linf))
+    return e;
+  *l2sq = l2 * l2;
+  return SPIRK_OK;
+}
 int spirk_problem_error_norms(spirk_ctx *, const spirk_level *lvl, const double *u, double t, double *l2, double *linf)
 {
   if (int e = check_level(lvl))
@@ -1083,6 +1149,22 @@ int spirk_comm_allreduce_sum(spirk_ctx *, spirk_comm *c, double *buf, long long 
   if (c->n_ranks > 1)
     g_cpu_allreduce(buf, n);
   return SPIRK_OK;
+}
+// the CPU double has no spatial partition (z-slabs are a feature of the CUDA library): a split keeps the whole group
+int spirk_comm_split(spirk_ctx *, spirk_comm *c, int, int, spirk_comm **out)
+{
+  if (c->n_ranks > 1)
+    return fail(SPIRK_ERR_UNSUPPORTED, "comm_split: not available on the CPU double");
+  *out = new spirk_comm{0, 1};
+  return SPIRK_OK;
+}
+int spirk_comm_allreduce_max(spirk_ctx *, spirk_comm *c, double *, long long)
+{
+  return c->n_ranks > 1 ? fail(SPIRK_ERR_UNSUPPORTED, "allreduce_max: not available on the CPU double") : SPIRK_OK;
+}
+int spirk_halo_exchange(spirk_ctx *, spirk_comm *, const spirk_level *lvl, int, double *, long long, int, int)
+{
+  return lvl->slab ? fail(SPIRK_ERR_UNSUPPORTED, "z-slab levels are not available on the CPU double") : SPIRK_OK;
 }
 int spirk_comm_allgather(spirk_ctx *, spirk_comm *c, double *recv, const double *send, long long n)
 {

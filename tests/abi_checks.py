@@ -219,6 +219,172 @@ def check_v3_full_size(dev, r, nb, opts=None, tol=RTOL):
     return errs
 
 
+# ------------------------------------------------------------------------------------------------------------
+# z-slab levels (spatial partition): every kernel on slab `c` of `C` against the slice of the oracle's result on
+# the whole mesh.  Runs on ONE device: the slabs are processed one after the other, the ghost planes a halo exchange would
+# bring are copied from the full arrays by the test; planes that no neighbour owns (below the first / above the last slab)
+# hold NaN, so any read of them poisons the result.
+PAD_HI = 1
+
+
+def slab_geometry(olv, k, c, C):
+    nc = olv.nc if hasattr(olv, "nc") else (olv.shape[0] - 1) // k
+    n1 = olv.shape[0]
+    L_lo, L_hi = nc * c // C, nc * (c + 1) // C
+    zo0, zo1 = k * L_lo, (n1 if L_hi == nc else k * L_hi)
+    return dict(nc=nc, n1=n1, L_lo=L_lo, L_hi=L_hi, zo0=zo0, zo1=zo1, pad_lo=2 * k, plane=n1 * n1)
+
+
+def slab_pack(full, gm):
+    """(nb, n1, n1, n1) -> per block [pad_lo | owned | pad_hi] planes; returns the flat buffer, the offset of the first owned
+    entry and the block stride"""
+    nb, n1 = full.shape[0], gm["n1"]
+    nz = gm["pad_lo"] + (gm["zo1"] - gm["zo0"]) + PAD_HI
+    buf = np.full((nb, nz, n1, n1), np.nan)
+    for lz in range(nz):
+        z = gm["zo0"] - gm["pad_lo"] + lz
+        if 0 <= z < n1:
+            buf[:, lz] = full[:, z]
+    return buf.reshape(-1), gm["pad_lo"] * gm["plane"], nz * gm["plane"]
+
+
+def slab_owned(flat, gm, nb):
+    nz = gm["pad_lo"] + (gm["zo1"] - gm["zo0"]) + PAD_HI
+    return flat.reshape(nb, nz, gm["n1"], gm["n1"])[:, gm["pad_lo"]:gm["pad_lo"] + gm["zo1"] - gm["zo0"]]
+
+
+class SlabBuf:
+    """device copy of a slab-local block vector"""
+
+    def __init__(self, ctx, full, gm):
+        flat, self.off, self.stride = slab_pack(full, gm)
+        self.ctx, self.gm, self.nb, self.size = ctx, gm, full.shape[0], flat.size
+        self.base = ctx.upload(flat)
+        self.ptr = C.c_void_p(self.base.value + 8 * self.off)
+
+    def owned(self):
+        return slab_owned(self.ctx.download(self.base, (self.size,)), self.gm, self.nb)
+
+
+def check_slab_kernels(dev, r, C_, nb=2, k=4):
+    dim = 3
+    _, olv = make_level(dim, k, r)
+    _, olc = make_level(dim, k, r - 1)
+    n1 = olv.shape[0]
+    mass = np.array(D4[:nb])
+    lap = np.full(nb, 0.1)
+    x, xo, b = block_input(olv, nb, 3, True), block_input(olv, nb, 4, True), block_input(olv, nb, 5, True)
+    bb = block_input(olv, nb, 6, False)
+    w = block_input(olv, nb, 7, False)
+    dinv = np.concatenate([olv.inverse_diagonal(m, 0.1) for m in mass])
+    f0, f1, f2 = np.array([0.7, 0.6, 0.65, 0.75][:nb]), np.array([0.3, 0.2, 0.25, 0.35][:nb]), np.array([1.1, 0.9, 1.0, 1.2][:nb])
+    bc = (slice(None),) + (None,) * 3
+    Ax = olv.apply(x, mass, lap)
+    Abb = olv.apply(bb, mass, lap)
+    x1 = f0[bc] * dinv * bb
+    x2 = x1 + f1[bc] * x1 + f2[bc] * dinv * (bb - olv.apply(x1, mass, lap))
+    cheb = x + f1[bc] * (x - xo) + f2[bc] * dinv * (b - Ax)
+    bz, wz = bb.copy(), w.copy()
+    bz[:, olv.bmask] = 0.0
+    wz[:, olv.bmask] = 0.0
+    km = olv.apply(bz, 0.0, lap) + olv.apply(wz, mass, 0.0)
+    km[:, olv.bmask] = bb[:, olv.bmask]
+    Cm = np.array([[5.0, 3.0], [-3.0, 5.0]])
+    u2 = block_input(olv, 2, 9, False)
+    v2 = u2.copy()
+    v2[:, olv.bmask] = 0.0
+    cpl = olv.apply(v2, 0.0, [0.1, 0.1]) + np.tensordot(Cm, olv.apply(v2, 1.0, 0.0), axes=(1, 0))
+    cpl[:, olv.bmask] = u2[:, olv.bmask]
+    g = so.GMG(dim, k, r, lambda lv: so.ScalarOp(lv))
+    uc = block_input(olc, nb, 11)
+    uf0 = block_input(olv, nb, 12)
+    prol = uf0 + g.prolongate(r, uc)
+    rest = g.restrict(r, bb)
+    prob = so.Problem(dim, k, r)
+    u_ex = prob.exact_nodal(0.3)
+    err_full = prob.errors(u_ex * 1.01, 0.3)
+    op = capi.real_op(mass, lap)
+    opc = capi.coupled_op(Cm, [0.1, 0.1])
+    pf0, _0 = capi.darr(f0)
+    pf1, _1 = capi.darr(f1)
+    pf2, _2 = capi.darr(f2)
+    pl, _3 = capi.darr(lap)
+    pm, _4 = capi.darr(mass)
+    l2sq_sum, linf_max, dot_sum = 0.0, 0.0, 0.0
+    for c in range(C_):
+        gm = slab_geometry(olv, k, c, C_)
+        gmc = dict(slab_geometry(olc, k, c, C_))
+        sl = (slice(None), slice(gm["zo0"], gm["zo1"]))
+        slc = (slice(None), slice(gmc["zo0"], gmc["zo1"]))
+        for coarse_replicated in (0, 1):
+            lvl = capi.Level(dim, k, 2 ** r, c | (C_ << 8) | (coarse_replicated << 16))
+            with capi.Context(dev) as ctx:
+                N = lvl_n = int(dev.lib.spirk_level_n_dofs(C.byref(lvl)))
+                assert N == (gm["zo1"] - gm["zo0"]) * gm["plane"]
+                tag = f"r={r} slab {c}/{C_} nb={nb}"
+                if coarse_replicated == 0:
+                    X, XO, B, BB, W, DI = (SlabBuf(ctx, a, gm) for a in (x, xo, b, bb, w, dinv))
+                    D1, D2 = SlabBuf(ctx, np.zeros_like(x), gm), SlabBuf(ctx, np.zeros_like(x), gm)
+                    st = X.stride
+                    ctx.call("spirk_op_apply", C.byref(lvl), C.byref(op), D1.ptr, X.ptr, st)
+                    got = D1.owned()
+                    if not relerr(got, Ax[sl]) < RTOL:  # which planes / rows / columns are off
+                        d = np.abs(got - Ax[sl])
+                        bad = np.argwhere(~(d < 1e-9 * np.max(np.abs(Ax))))
+                        raise AssertionError(f"{tag} apply: {len(bad)} entries off; blocks {sorted(set(bad[:, 0]))}, local planes "
+                                             f"{sorted(set(bad[:, 1]))}, rows {sorted(set(bad[:, 2]))[:12]}, columns {sorted(set(bad[:, 3]))[:12]}; "
+                                             f"first {bad[0].tolist()}: {got[tuple(bad[0])]} vs {Ax[sl][tuple(bad[0])]}")
+                    ctx.call("spirk_op_residual", C.byref(lvl), C.byref(op), D1.ptr, B.ptr, X.ptr, st)
+                    assert relerr(D1.owned(), (b - Ax)[sl]) < RTOL, tag + " residual"
+                    ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), D1.ptr, X.ptr, XO.ptr, B.ptr, DI.ptr, st, pf1, pf2)
+                    assert relerr(D1.owned(), cheb[sl]) < RTOL, tag + " cheb (explicit diagonal)"
+                    ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), D1.ptr, X.ptr, XO.ptr, B.ptr, None, st, pf1, pf2)
+                    assert relerr(D1.owned(), cheb[sl]) < RTOL, tag + " cheb (own diagonal)"
+                    ctx.call("spirk_op_cheb_first", C.byref(lvl), C.byref(op), D1.ptr, D2.ptr, BB.ptr, st, pf0, pf1, pf2)
+                    assert relerr(D1.owned(), x1[sl]) < RTOL and relerr(D2.owned(), x2[sl]) < RTOL, tag + " cheb_first"
+                    ctx.call("spirk_op_apply_km", C.byref(lvl), nb, D1.ptr, BB.ptr, W.ptr, st, pl, pm)
+                    assert relerr(D1.owned(), km[sl]) < RTOL, tag + " apply_km"
+                    U2, DC = SlabBuf(ctx, u2, gm), SlabBuf(ctx, np.zeros_like(u2), gm)
+                    ctx.call("spirk_op_apply", C.byref(lvl), C.byref(opc), DC.ptr, U2.ptr, U2.stride)
+                    assert relerr(DC.owned(), cpl[sl]) < RTOL, tag + " coupled pair"
+                    # setup / problem kernels on the owned range (single block)
+                    ctx.call("spirk_op_inverse_diagonal", C.byref(lvl), D1.ptr, 16.0, 0.1)
+                    assert relerr(D1.owned()[:1], olv.inverse_diagonal(16.0, 0.1)[sl]) < RTOL, tag + " inverse diagonal"
+                    ctx.call("spirk_problem_rhs_spatial", C.byref(lvl), D1.ptr)
+                    assert relerr(D1.owned()[:1], prob.rspace[sl]) < 1e-12, tag + " rhs"
+                    ctx.call("spirk_problem_interpolate_solution", C.byref(lvl), D1.ptr, 0.3)
+                    assert relerr(D1.owned()[:1], u_ex[sl]) < 1e-12, tag + " interpolation"
+                    UE = SlabBuf(ctx, u_ex * 1.01, gm)
+                    l2, li = C.c_double(), C.c_double()
+                    ctx.call("spirk_problem_error_norms_partial", C.byref(lvl), UE.ptr, 0.3, C.byref(l2), C.byref(li))
+                    l2sq_sum += l2.value
+                    linf_max = max(linf_max, li.value)
+                    ctx.call("spirk_constraints_set_zero", C.byref(lvl), nb, BB.ptr, BB.stride)
+                    assert np.array_equal(BB.owned(), bz[sl]), tag + " set_zero"
+                    dot_sum += ctx.scalar_call("spirk_vec_dot_strided", X.ptr, B.ptr, N, nb, st)
+                # transfers: the coarse vector as a slab of the coarse level, or held in full (agglomerated coarse levels)
+                F0, FB = SlabBuf(ctx, uf0, gm), SlabBuf(ctx, bb, gm)
+                if coarse_replicated:
+                    dc = ctx.upload(uc)
+                    ctx.call("spirk_mg_prolongate_add", C.byref(lvl), nb, F0.ptr, F0.stride, dc, olc.N)
+                    assert relerr(F0.owned(), prol[sl]) < RTOL, tag + " prolongation from a replicated coarse level"
+                    dr = ctx.upload(np.full_like(uc, np.nan))
+                    ctx.call("spirk_mg_restrict", C.byref(lvl), nb, dr, olc.N, FB.ptr, FB.stride)
+                    out = ctx.download(dr, uc.shape)
+                    assert relerr(out[slc], rest[slc]) < RTOL, tag + " restriction into a replicated coarse level"
+                    lo, hi = gmc["zo0"], gmc["zo1"]
+                    assert np.all(np.isnan(out[:, :lo])) and np.all(np.isnan(out[:, hi:])), tag + " restriction wrote outside its planes"
+                else:
+                    UC = SlabBuf(ctx, uc, gmc)
+                    ctx.call("spirk_mg_prolongate_add", C.byref(lvl), nb, F0.ptr, F0.stride, UC.ptr, UC.stride)
+                    assert relerr(F0.owned(), prol[sl]) < RTOL, tag + " prolongation"
+                    RC = SlabBuf(ctx, np.full_like(uc, np.nan), gmc)
+                    ctx.call("spirk_mg_restrict", C.byref(lvl), nb, RC.ptr, RC.stride, FB.ptr, FB.stride)
+                    assert relerr(RC.owned(), rest[slc]) < RTOL, tag + " restriction"
+    assert abs(np.sqrt(l2sq_sum) - err_full[0]) < 1e-9 * err_full[0] and abs(linf_max - err_full[1]) < 1e-9 * err_full[1]
+    assert abs(dot_sum - float(np.sum(x * b))) < 1e-9 * np.sqrt(x.size)
+
+
 def check_inverse_diagonal(dev, dim, k, r, mass=16.0, lap=0.1):
     lvl, olv = make_level(dim, k, r)
     with capi.Context(dev) as ctx:

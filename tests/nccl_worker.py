@@ -6,6 +6,7 @@ import json
 import os
 import sys
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -38,7 +39,24 @@ def main():
         while not run.finished():
             run.step()
         run.finish()
-        res = {"u": run.solution().tolist() if r <= 4 else None, "outer": run.array("outer_iterations").tolist(),
+        # the solution of the whole mesh: with a spatial partition the ranks of stage 0 hold the z-slabs, in rank order
+        u = None
+        if r <= 4:
+            mine = torch.from_numpy(run.solution()).cuda()
+            first = int(run.scalar("first_owned"))
+            info = torch.tensor([first, mine.numel()], dtype=torch.int64, device="cuda")
+            infos = [torch.zeros_like(info) for _ in range(world)]
+            dist.all_gather(infos, info)
+            nmax = max(int(i[1]) for i in infos)
+            pad = torch.zeros(nmax, dtype=torch.float64, device="cuda")
+            pad[:mine.numel()] = mine
+            parts = [torch.zeros_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            full = np.zeros(int(run.scalar("n_dofs")))
+            for i, p in zip(infos, parts):
+                full[int(i[0]):int(i[0]) + int(i[1])] = p[:int(i[1])].cpu().numpy()
+            u = full.tolist()
+        res = {"u": u, "outer": run.array("outer_iterations").tolist(),
                "error_L2": run.array("error_L2").tolist(), "error_Linf": run.array("error_Linf").tolist(),
                "norm": run.array("solution_l2").tolist(), "launches": run.scalar("launch_count")}
     if rank == 0:

@@ -124,3 +124,9 @@ def test_op_apply_km(gpu_dev, dim, k, r, nb, opts):
 @pytest.mark.parametrize("dim,k,r", [(3, 4, 5), (3, 4, 6)])
 def test_transfer_full_size(gpu_dev, dim, k, r):
     ac.check_transfer(gpu_dev, dim, k, r)
+
+
+@pytest.mark.parametrize("r,C,nb", [(3, 2, 2), (4, 2, 1), (4, 4, 2), (5, 2, 2), (5, 4, 1), (6, 2, 1)])
+def test_slab_kernels(gpu_dev, r, C, nb):
+    """z-slab levels (spatial partition): every kernel on every slab against the slice of the whole-mesh oracle result"""
+    ac.check_slab_kernels(gpu_dev, r, C, nb)

@@ -90,3 +90,27 @@ def test_spirk_ranks_equal_single_gpu_at_baseline_size(tmp_path, gpu_dev):
     assert np.allclose(two["norm"], one["norm"], rtol=1e-10, atol=0)
     assert np.allclose(two["error_L2"], one["error_L2"], rtol=1e-6, atol=0)
     assert np.all(np.abs(np.array(two["outer"]) - one["outer"]) <= 1), (two["outer"], one["outer"])
+
+
+# ---- spatial partition (z-slabs over the column communicator, halo exchange, replicated coarse levels): SURVEY 8e
+@pytest.mark.parametrize("scheme,k,r,q", [("irk", 4, 3, 2), ("irk", 4, 4, 2), ("ost", 4, 3, 0)])
+def test_two_slabs_match_oracle(tmp_path, scheme, k, r, q):
+    """1 stage rank x 2 space ranks: the whole hierarchy down to 8 cells per direction is split into two z-slabs"""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    res = run_ranks(tmp_path, 2, scheme, 3, k, r, q)
+    if scheme == "ost":
+        ora = so.run(scheme, 3, k, r, q, 0.1, 0.5, outer_tol=1e-12)
+        uo = ora["u"].reshape(-1)
+        assert np.max(np.abs(np.array(res["u"]) - uo)) < 1e-8 * np.max(np.abs(uo))  # CG to 1e-8 |rhs| (main.cc:526)
+    else:
+        compare_with_oracle(res, scheme, 3, k, r, q)
+
+
+@pytest.mark.parametrize("r,q", [(3, 2), (4, 2)])
+def test_stage_x_space_grid_four_gpus(tmp_path, r, q):
+    """spirk with q = 2 stage ranks x 2 space ranks on 4 GPUs (the reference's rectangular grid, main.cc:3660-3698)"""
+    if n_gpus() < 4:
+        pytest.skip("needs 4 GPUs (run with gpurun --gpus 4)")
+    res = run_ranks(tmp_path, 4, "spirk", 3, 4, r, q)
+    compare_with_oracle(res, "spirk", 3, 4, r, q)

@@ -58,3 +58,14 @@ def test_gmg_benchmark_modes(cpu_host):
     # the reference's gmg.cc benchmark (1 component / n components / n groups / batched)
     hc.check_gmg_benchmark(cpu_host, 2, 2, 3)
     hc.check_gmg_benchmark(cpu_host, 3, 4, 1, n_components=2)
+
+
+def test_dealii_renumbering_glue(tmp_path):
+    """INTEGRATION.md route A: dealii_spirk_b200/host/dealii_glue.h maps a (mock) deal.II support-point map to the library's
+    lexicographic numbering for every degree, 2-D and 3-D (reference DoF distribution: main.cc:3374-3412)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "glue_check")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "glue_check.cc")])
+    assert "glue ok" in subprocess.run([exe], capture_output=True, text=True, check=True).stdout
