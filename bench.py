@@ -181,15 +181,17 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = a.gpus
     q = a.stages or (2 if n_gpus == 1 else 8)
-    if q % n_gpus:
-        raise SystemExit(f"--stages {q} must be a multiple of --gpus {n_gpus}")
+    if q % n_gpus and n_gpus % q:
+        raise SystemExit(f"--stages {q} and --gpus {n_gpus}: one must divide the other")
     scheme = a.scheme or ("irk" if n_gpus == 1 else "spirk")
     metric = "implicit RK time step: stage-DoFs advanced per second (n_dofs*q/step time); ms_per_step = time per SPIRK step"
     unit = "GDoF*stage/s"
     config = {"workload": f"3D heat equation Q{a.degree}, {scheme} q={q}, GMG(Chebyshev 5)+GMRES, hypercube r={a.refine}",
               "n_dofs": (a.degree * 2 ** a.refine + 1) ** 3, "stages": q, "refine": a.refine, "degree": a.degree,
               "outer_tolerance": a.outer_tolerance, "dt": 0.1,
-              "parallelism": "1 GPU, stages batched" if n_gpus == 1 else f"stage-parallel: {q // n_gpus} stage(s) per GPU x {n_gpus}",
+              "parallelism": "1 GPU, stages batched" if n_gpus == 1 else (
+                  f"stage-parallel: {q // n_gpus} stage(s) per GPU x {n_gpus}" if q % n_gpus == 0 else
+                  f"stage x space grid: {q} stage ranks x {n_gpus // q} z-slabs of the mesh"),
               "l2_policy": "working set (>= 30 vectors of n_dofs*8 B) exceeds the 126 MB L2; no explicit flush"}
 
     if a.impl == "reference":
@@ -312,7 +314,7 @@ def main():
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         lvl = capi.Level(3, a.degree, 2 ** a.refine, 0)
         N = lvl.n_dofs
-        m = q if n_gpus == 1 else q // n_gpus
+        m = q if n_gpus == 1 else max(1, q // n_gpus)
         with capi.Context(dev, local_rank) as ctx:
             x, xo, rhs, dinv, dst = (ctx.alloc(m * N) for _ in range(5))
             ctx.call("spirk_vec_set", x, m * N, 0.5)

@@ -178,8 +178,14 @@ namespace spirk_host
         // Spatial partition (the reference's triangulation on comm_column, main.cc:3027, 3478): level l is split into z-slabs
         // when the plane-streaming cell operator covers it and every slab keeps an even number of cell layers (so that the
         // next coarser level splits at the same planes); coarser levels are held in full by every rank of the column.
-        const int  C = comm_column.size;
-        const auto partitioned = [&](unsigned int l) { return C > 1 && dim == 3 && k == 4 && (1u << l) >= 8 && (1u << l) % (2 * C) == 0; };
+        // Levels with fewer than SPIRK_SLAB_MIN_CELLS (default 32) cells per direction are replicated as well: their kernels
+        // are latency bound, a halo exchange per operator application would cost more than repeating the work.
+        const int          C = comm_column.size;
+        const char        *mc = std::getenv("SPIRK_SLAB_MIN_CELLS");
+        const unsigned int min_cells = std::max(8, mc ? std::atoi(mc) : 32);
+        const auto partitioned = [&](unsigned int l) {
+          return C > 1 && dim == 3 && k == 4 && (1u << l) >= std::min(min_cells, 1u << r) && (1u << l) >= 8 && (1u << l) % (2 * C) == 0;
+        };
         if (C > 1 && !partitioned(r))
           throw Error("spatial partition: needs 3-D, FEDegree 4 and 2^NRefinements a multiple of twice the number of slabs (>= 8 cells)");
         if (C > 1 && (scheme.rfind("complex", 0) == 0 || scheme == "irk_batched" || comm_row.size * 1u != ((scheme == "spirk") ? q : 1u)))

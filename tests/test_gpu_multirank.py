@@ -93,12 +93,14 @@ def test_spirk_ranks_equal_single_gpu_at_baseline_size(tmp_path, gpu_dev):
 
 
 # ---- spatial partition (z-slabs over the column communicator, halo exchange, replicated coarse levels): SURVEY 8e
-@pytest.mark.parametrize("scheme,k,r,q", [("irk", 4, 3, 2), ("irk", 4, 4, 2), ("ost", 4, 3, 0)])
-def test_two_slabs_match_oracle(tmp_path, scheme, k, r, q):
-    """1 stage rank x 2 space ranks: the whole hierarchy down to 8 cells per direction is split into two z-slabs"""
+# SPIRK_SLAB_MIN_CELLS = 8: every level down to 8 cells per direction is split (slab -> slab transfers with halo exchange on
+# both levels); default 32: the levels below the finest are replicated (slab -> replicated transfers with the all-gather)
+@pytest.mark.parametrize("scheme,k,r,q,min_cells", [("irk", 4, 3, 2, "8"), ("irk", 4, 4, 2, "8"), ("irk", 4, 4, 2, None), ("ost", 4, 3, 0, None)])
+def test_two_slabs_match_oracle(tmp_path, scheme, k, r, q, min_cells):
+    """1 stage rank x 2 space ranks: the mesh hierarchy is split into two z-slabs"""
     if n_gpus() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    res = run_ranks(tmp_path, 2, scheme, 3, k, r, q)
+    res = run_ranks(tmp_path, 2, scheme, 3, k, r, q, env_extra={"SPIRK_SLAB_MIN_CELLS": min_cells} if min_cells else None)
     if scheme == "ost":
         ora = so.run(scheme, 3, k, r, q, 0.1, 0.5, outer_tol=1e-12)
         uo = ora["u"].reshape(-1)
@@ -107,10 +109,10 @@ def test_two_slabs_match_oracle(tmp_path, scheme, k, r, q):
         compare_with_oracle(res, scheme, 3, k, r, q)
 
 
-@pytest.mark.parametrize("r,q", [(3, 2), (4, 2)])
-def test_stage_x_space_grid_four_gpus(tmp_path, r, q):
+@pytest.mark.parametrize("r,q,min_cells", [(3, 2, None), (4, 2, "8")])
+def test_stage_x_space_grid_four_gpus(tmp_path, r, q, min_cells):
     """spirk with q = 2 stage ranks x 2 space ranks on 4 GPUs (the reference's rectangular grid, main.cc:3660-3698)"""
     if n_gpus() < 4:
         pytest.skip("needs 4 GPUs (run with gpurun --gpus 4)")
-    res = run_ranks(tmp_path, 4, "spirk", 3, 4, r, q)
+    res = run_ranks(tmp_path, 4, "spirk", 3, 4, r, q, env_extra={"SPIRK_SLAB_MIN_CELLS": min_cells} if min_cells else None)
     compare_with_oracle(res, "spirk", 3, 4, r, q)
