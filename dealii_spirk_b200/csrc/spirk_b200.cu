@@ -789,6 +789,8 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
       SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy, ncc), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, t2, wz.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
       const long long rpb = (long long)nf * zf, rows = rpb * nb;
+      if (smem_x > 48 * 1024)
+        SPIRK_DISPATCH_K(g.k, SPIRK_CUDA(cudaFuncSetAttribute(k_prolongate_x_add<K, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x)));
       SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, fine, fs, t1, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
@@ -802,6 +804,8 @@ int spirk_mg_prolongate_add(spirk_ctx *ctx, const spirk_level *lf, int nb, doubl
       SPIRK_DISPATCH_K(g.k, (k_prolongate_1d<K><<<grid_1d(wy, ncc), 256, 0, ctx->stream>>>(wy, t1, wy.N_out, coarse, cs)));
       SPIRK_LAUNCH_CHECK(ctx);
       const long long rpb = nf, rows = rpb * nb;
+      if (smem_x > 48 * 1024)
+        SPIRK_DISPATCH_K(g.k, SPIRK_CUDA(cudaFuncSetAttribute(k_prolongate_x_add<K, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x)));
       SPIRK_DISPATCH_K(g.k, (k_prolongate_x_add<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, fine, fs, t1, wy.N_out)));
       SPIRK_LAUNCH_CHECK(ctx);
@@ -857,6 +861,8 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
         return e;
       double         *t1 = ctx->d_scratch, *t2 = ctx->d_scratch + (size_t)nb * wx.N_out;
       const long long rpb = (long long)nf * zin, rows = rpb * nb;
+      if (smem_x > 48 * 1024) // (r >= 7: eight fine + coarse rows exceed the default dynamic shared-memory limit)
+        SPIRK_DISPATCH_K(g.k, SPIRK_CUDA(cudaFuncSetAttribute(k_restrict_x<K, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x)));
       SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, t1, wx.N_out, fine - (long long)g.gh_lo * g.plane, fs)));
       SPIRK_LAUNCH_CHECK(ctx);
@@ -872,6 +878,8 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
         return e;
       double         *t1 = ctx->d_scratch;
       const long long rpb = nf, rows = rpb * nb;
+      if (smem_x > 48 * 1024)
+        SPIRK_DISPATCH_K(g.k, SPIRK_CUDA(cudaFuncSetAttribute(k_restrict_x<K, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x)));
       SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
                               nf, ncc, rows, rpb, t1, wx.N_out, fine, fs)));
       SPIRK_LAUNCH_CHECK(ctx);

@@ -327,10 +327,228 @@ namespace
     }
   };
 
+  // ---------------------------------------------------------------------------------------------------------
+  // Vectorised cell loop: what deal.II's MatrixFree does on a CPU - batches of VL = 8 cells in
+  // structure-of-arrays layout (one AVX-512 lane per cell, VectorizedArray<double>), sum factorisation with compile-time
+  // extents: interpolate to the Gauss points (dim sweeps), collocation derivative / scaling by JxW and J^-T J^-1 /
+  // transposed derivative (2 dim sweeps), integrate (dim sweeps); the mass term and the coupling of the blocks are mixed
+  // at the quadrature points (operator.h:639-647).  Threads: rows of cells along x, coloured by the parity of the other
+  // cell indices so that concurrently processed rows share no DoF.
+  constexpr int VL = 8;
+  template <int n, int dim>
+  struct FastCell
+  {
+    static constexpr int nl = (dim == 3) ? n * n * n : n * n;
+    // out[.., r, ..] = sum_j A[r][j] (or A[j][r]) in[.., j, ..] along direction d, for all VL lanes
+    template <bool transpose, bool add, int d>
+    static inline void sweep(const double *__restrict__ A, const double (*__restrict__ in)[VL], double (*__restrict__ out)[VL])
+    {
+      constexpr int pre = (d == 0) ? 1 : (d == 1 ? n : n * n), post = nl / (pre * n);
+      for (int o = 0; o < post; ++o)
+        for (int i = 0; i < pre; ++i)
+          for (int r = 0; r < n; ++r)
+            {
+              double s[VL];
+#pragma omp simd
+              for (int l = 0; l < VL; ++l)
+                s[l] = 0.0;
+              for (int j = 0; j < n; ++j)
+                {
+                  const double a = transpose ? A[j * n + r] : A[r * n + j];
+#pragma omp simd
+                  for (int l = 0; l < VL; ++l)
+                    s[l] += a * in[(o * n + j) * pre + i][l];
+                }
+#pragma omp simd
+              for (int l = 0; l < VL; ++l)
+                out[(o * n + r) * pre + i][l] = add ? out[(o * n + r) * pre + i][l] + s[l] : s[l];
+            }
+    }
+  };
+
+  template <int n, int dim>
+  void cell_loop_fast(const Geo &geo, const spirk_opdesc *op, double *dst, const double *src, long long stride)
+  {
+    using FC          = FastCell<n, dim>;
+    constexpr int nl  = FC::nl;
+    const FE     &fe  = get_fe(geo.k);
+    const int     k = geo.k, nc = geo.nc, n1 = geo.n1, nb = op->nb;
+    const double  jxw = std::pow(geo.h, dim), gs = 1.0 / (geo.h * geo.h);
+    double        w3[nl];
+    for (int q = 0; q < nl; ++q)
+      {
+        int    r = q;
+        double w = 1;
+        for (int d = 0; d < dim; ++d)
+          w *= fe.wq[r % n], r /= n;
+        w3[q] = w * jxw;
+      }
+    const double *B = fe.B.data(), *D = fe.Dcol.data();
+    const int     nrows = (dim == 3) ? nc * nc : nc; // rows of cells along x
+    for (int colour = 0; colour < (dim == 3 ? 4 : 2); ++colour)
+      {
+#pragma omp parallel
+        {
+          // per thread: values at the nodes / quadrature points of every block, work arrays
+          std::vector<double> store((size_t)(2 * nb + 4) * nl * VL);
+          auto                arr = [&](int i) { return reinterpret_cast<double(*)[VL]>(store.data() + (size_t)i * nl * VL); };
+          double(*t0)[VL] = arr(2 * nb), (*t1)[VL] = arr(2 * nb + 1), (*acc)[VL] = arr(2 * nb + 2), (*gq)[VL] = arr(2 * nb + 3);
+#pragma omp for schedule(dynamic, 1)
+          for (int row = 0; row < nrows; ++row)
+            {
+              const int cy = (dim == 3) ? row % nc : row, cz = (dim == 3) ? row / nc : 0;
+              if ((cy & 1) + 2 * (cz & 1) != colour)
+                continue;
+              for (int cx0 = 0; cx0 < nc; cx0 += VL)
+                {
+                  const int nv = std::min(VL, nc - cx0);
+                  // gather (Dirichlet DoFs read as zero) and interpolate every block to the Gauss points
+                  for (int b = 0; b < nb; ++b)
+                    {
+                      double(*u)[VL] = arr(b), (*vq)[VL] = arr(nb + b);
+                      for (int l = 0; l < nl; ++l)
+                        {
+                          const int lx = l % n, ly = (l / n) % n, lz = (dim == 3) ? l / (n * n) : 0;
+                          const int iy = cy * k + ly, iz = (dim == 3) ? cz * k + lz : 0;
+                          const bool bd_yz = iy == 0 || iy == n1 - 1 || (dim == 3 && (iz == 0 || iz == n1 - 1));
+                          const double *p  = src + b * stride + (long long)n1 * (iy + (long long)n1 * iz);
+                          for (int v = 0; v < VL; ++v)
+                            {
+                              const int ix = (cx0 + v) * k + lx;
+                              u[l][v]      = (v < nv && !bd_yz && ix != 0 && ix != n1 - 1) ? p[ix] : 0.0;
+                            }
+                        }
+                      FC::template sweep<false, false, 0>(B, u, t0);
+                      if constexpr (dim == 3)
+                        {
+                          FC::template sweep<false, false, 1>(B, t0, t1);
+                          FC::template sweep<false, false, 2>(B, t1, vq);
+                        }
+                      else
+                        FC::template sweep<false, false, 1>(B, t0, vq);
+                    }
+                  for (int b = 0; b < nb; ++b)
+                    {
+                      double(*vq)[VL] = arr(nb + b);
+                      // mass term at the quadrature points: mass_b v_b, or sum_j C_bj v_j for coupled operators
+                      for (int q = 0; q < nl; ++q)
+                        {
+#pragma omp simd
+                          for (int v = 0; v < VL; ++v)
+                            acc[q][v] = 0.0;
+                        }
+                      for (int j = 0; j < nb; ++j)
+                        {
+                          const double c = (op->kind == SPIRK_OP_REAL) ? (j == b ? op->mass[b] : 0.0) : op->coupling[b * nb + j];
+                          if (c == 0.0)
+                            continue;
+                          double(*vj)[VL] = arr(nb + j);
+                          for (int q = 0; q < nl; ++q)
+                            {
+                              const double cw = c * w3[q];
+#pragma omp simd
+                              for (int v = 0; v < VL; ++v)
+                                acc[q][v] += cw * vj[q][v];
+                            }
+                        }
+                      const double lap = op->laplace[b];
+                      if (lap != 0.0)
+                        {
+                          const auto scale = [&]() {
+                            for (int q = 0; q < nl; ++q)
+                              {
+                                const double cw = lap * w3[q] * gs;
+#pragma omp simd
+                                for (int v = 0; v < VL; ++v)
+                                  gq[q][v] *= cw;
+                              }
+                          };
+                          FC::template sweep<false, false, 0>(D, vq, gq);
+                          scale();
+                          FC::template sweep<true, true, 0>(D, gq, acc);
+                          FC::template sweep<false, false, 1>(D, vq, gq);
+                          scale();
+                          FC::template sweep<true, true, 1>(D, gq, acc);
+                          if constexpr (dim == 3)
+                            {
+                              FC::template sweep<false, false, 2>(D, vq, gq);
+                              scale();
+                              FC::template sweep<true, true, 2>(D, gq, acc);
+                            }
+                        }
+                      // integrate and scatter (constrained DoFs skipped); lanes one after the other: neighbouring cells of the
+                      // batch share their x-face DoFs
+                      double(*out)[VL] = arr(b); // (the nodal values of block b are no longer needed)
+                      if constexpr (dim == 3)
+                        {
+                          FC::template sweep<true, false, 0>(B, acc, t0);
+                          FC::template sweep<true, false, 1>(B, t0, t1);
+                          FC::template sweep<true, false, 2>(B, t1, out);
+                        }
+                      else
+                        {
+                          FC::template sweep<true, false, 0>(B, acc, t0);
+                          FC::template sweep<true, false, 1>(B, t0, out);
+                        }
+                      for (int l = 0; l < nl; ++l)
+                        {
+                          const int lx = l % n, ly = (l / n) % n, lz = (dim == 3) ? l / (n * n) : 0;
+                          const int iy = cy * k + ly, iz = (dim == 3) ? cz * k + lz : 0;
+                          if (iy == 0 || iy == n1 - 1 || (dim == 3 && (iz == 0 || iz == n1 - 1)))
+                            continue;
+                          double *p = dst + b * stride + (long long)n1 * (iy + (long long)n1 * iz);
+                          for (int v = 0; v < nv; ++v)
+                            {
+                              const int ix = (cx0 + v) * k + lx;
+                              if (ix != 0 && ix != n1 - 1)
+                                p[ix] += out[l][v];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+      }
+  }
+
   // the matrix-free cell loop (ref operator.h:298-310 + 379-421 / 616-665 / 841-880)
   void cell_loop(const spirk_level *lvl, const spirk_opdesc *op, double *dst, const double *src, long long stride)
   {
     const Geo geo(lvl);
+    if (!std::getenv("SPIRK_CPU_SCALAR_CELLS"))
+      {
+        // zero dst, vectorised cell batches, identity on constrained DoFs (below)
+        for (int b = 0; b < op->nb; ++b)
+          {
+            double *d = dst + b * stride;
+#pragma omp parallel for
+            for (long long i = 0; i < geo.N; ++i)
+              d[i] = 0.0;
+          }
+#define SPIRK_FAST(NN)                                                        \
+  case NN:                                                                    \
+    if (geo.dim == 3)                                                         \
+      cell_loop_fast<NN, 3>(geo, op, dst, src, stride);                       \
+    else                                                                      \
+      cell_loop_fast<NN, 2>(geo, op, dst, src, stride);                       \
+    break;
+        switch (geo.n)
+          {
+            SPIRK_FAST(2) SPIRK_FAST(3) SPIRK_FAST(4) SPIRK_FAST(5) SPIRK_FAST(6) SPIRK_FAST(7)
+          }
+#undef SPIRK_FAST
+        for (int b = 0; b < op->nb; ++b)
+          {
+#pragma omp parallel for
+            for (long long i = 0; i < geo.N; ++i)
+              {
+                const int ix = i % geo.n1, iy = (i / geo.n1) % geo.n1, iz = (geo.dim == 3) ? i / ((long long)geo.n1 * geo.n1) : 0;
+                if (geo.on_boundary(ix, iy, iz))
+                  dst[b * stride + i] = src[b * stride + i];
+              }
+          }
+        return;
+      }
     const int dim = geo.dim, n = geo.n, k = geo.k, nc = geo.nc, n1 = geo.n1, nb = op->nb;
     const long long N = geo.N;
     int nl = 1;

@@ -121,9 +121,11 @@ def test_op_apply_km(gpu_dev, dim, k, r, nb, opts):
     ac.check_apply_km(gpu_dev, dim, k, r, nb, opts)
 
 
-@pytest.mark.parametrize("dim,k,r", [(3, 4, 5), (3, 4, 6)])
-def test_transfer_full_size(gpu_dev, dim, k, r):
-    ac.check_transfer(gpu_dev, dim, k, r)
+@pytest.mark.parametrize("dim,k,r,nb", [(3, 4, 5, 2), (3, 4, 6, 2), (2, 6, 7, 1), (2, 4, 8, 2)])
+def test_transfer_full_size(gpu_dev, dim, k, r, nb):
+    """incl. rows of 769 / 1025 nodes: the staged rows of the x sweeps exceed the default dynamic shared-memory limit (as on the
+    3-D r = 7 level, 513 nodes per row)"""
+    ac.check_transfer(gpu_dev, dim, k, r, nb)
 
 
 @pytest.mark.parametrize("r,C,nb", [(3, 2, 2), (4, 2, 1), (4, 4, 2), (5, 2, 2), (5, 4, 1), (6, 2, 1)])

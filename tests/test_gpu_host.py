@@ -65,3 +65,19 @@ def test_gmg_benchmark_modes(gpu_host):
     """the reference's gmg.cc benchmark modes on the GPU: iteration counts as the oracle"""
     hc.check_gmg_benchmark(gpu_host, 3, 4, 2, n_components=3)
     hc.check_gmg_benchmark(gpu_host, 2, 2, 4, n_components=8)
+
+
+def test_baseline_size_against_oracle_fixture(gpu_host):
+    """BASELINE configs[1] at r = 5 (3-D Q4, IRK q = 2, 2 146 689 DoFs x 2 stages): the CUDA path against the NumPy oracle's
+    answer committed in tests/golden/baseline_size_irk_q2_r5.json (tools/make_golden_baseline_size.py; the oracle needs
+    minutes for this size): solution 1e-10, error norms, solution norm, outer iteration counts +-1."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "baseline_size_irk_q2_r5.json")))
+    res = hc.run_host(gpu_host, g["scheme"], g["dim"], g["k"], g["r"], g["q"], tol=g["outer_tol"], end=g["end"])
+    us = res["u"][::g["sample_stride"]]
+    assert np.max(np.abs(us - np.array(g["u_sample"]))) < 1e-10 * g["u_max"]
+    eo = np.array(g["errors"])
+    assert np.allclose(res["error_L2"], eo[:, 0], rtol=1e-7, atol=0) and np.allclose(res["error_Linf"], eo[:, 1], rtol=1e-7, atol=0)
+    assert np.allclose(res["norm"][1:], g["norms"], rtol=1e-10, atol=0)
+    assert np.all(np.abs(res["outer"] - np.array(g["n_outer"])) <= 1), (res["outer"], g["n_outer"])
