@@ -49,6 +49,16 @@ namespace spirk
 {
   __host__ __device__ constexpr int v3_nops(const int mode) { return mode == V2_RESIDUAL ? 1 : (mode == V2_CHEB_OWN ? 2 : 0); }
 
+  // rows handled side by side by the epilogue pre-pass: the largest divisor of oy that is a multiple of k, even, and <= avail
+  __host__ __device__ constexpr int v3_pre_rows(const int avail, const int oy, const int k)
+  {
+    int best = 0;
+    for (int r = k; r <= oy && r <= avail; r += k)
+      if (oy % r == 0 && r % 2 == 0)
+        best = r;
+    return best;
+  }
+
   template <int K, int TX, int TY, int MODE, int NPT = K, int NBC = 1>
   struct CfgV3
   {
@@ -160,6 +170,9 @@ namespace spirk
     int           zo0;            // global index of the first owned node plane = local plane 0 of every vector
     int           gh_lo;          // ghost planes below the owned range (the tensor maps start there)
     int           sh_src, sh_o0, sh_o1; // element shift of the 16-byte aligned map base below the vector
+    int           pb[SPIRK_MAX_BLOCKS]; // parity of the global row of staged row 0 of an EVEN node plane of block b (set by
+                                        // v3_launch_mode; K and the tile origins are even, n1 is odd: the parity alternates
+                                        // from plane to plane and is a compile-time function of the plane's position ZL)
     alignas(64) CUtensorMap tm_src, tm_o0, tm_o1; // staged nodes; operand 0 (rhs | x_old); operand 1 (rhs)
   };
 
@@ -234,6 +247,7 @@ namespace spirk
 #define KC(i, j) kp[v3_cidx<K>(i, j)]
 
     const int       tid = threadIdx.x;
+    const int       wrp = __shfl_sync(0xffffffffu, tid >> 5, 0); // warp index, provably warp-uniform
     const int       n1 = a.g.n1, nc = a.g.nc;
     const long long plane = (long long)n1 * n1;
     const int       ncols = a.ntx * a.nty;
@@ -276,7 +290,8 @@ namespace spirk
             if (tid == 0)
               QS[0] = atomicAdd(a.sched, 1);
             __syncthreads();
-            const int item = QS[0];
+            const int item = __shfl_sync(0xffffffffu, QS[0], 0); // (warp-uniform by construction: lets the compiler keep the piece's
+                                                                 // indices and the per-block coefficients in uniform registers)
             if (item >= a.n_items)
               break;
             col            = item % ncols;
@@ -347,6 +362,8 @@ namespace spirk
               const bool      owned = (NOPS > 0) && !zpl && (P >= K * L0) && (P < K * L1);
               const unsigned  bar   = bar_u32 + 8 * slot, dst = ring_u32 + slot * (SLOT * 8);
               const long long Rb    = Rb0 + (long long)n1 * sidx, Ro = Rb + K;
+              if (MODE == V2_CHEB_OWN) // the slot was written through the generic proxy (g over rhs)
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
               mbar_arrive_expect_tx(bar, (zpl ? 0u : C::BYTES_U) + (owned ? ((has_o0 ? 1u : 0u) + (NOPS == 2 ? 1u : 0u)) * C::BYTES_O : 0u));
               if (!zpl)
                 {
@@ -358,26 +375,30 @@ namespace spirk
                       const long long    Rj  = (NBC == 1 || a.km) ? Rb : Rb + (long long)(j - b) * a.rows_per_block;
                       const CUtensorMap *tm  = second ? &a.tm_o0 : &a.tm_src;
                       const int          shj = second ? a.sh_o0 : a.sh_src;
-                      tma_g2s_2d(dst + j * (2 * UB * 8), tm, (gx0 - K + shj) & ~1, (int)((Rj + 1) >> 1), bar);
-                      tma_g2s_2d(dst + j * (2 * UB * 8) + UB * 8, tm, (n1 + gx0 - K + shj) & ~1, (int)(Rj >> 1), bar);
+                      // box t = the staged rows of parity t (global rows Rj + t, Rj + t + 2, ...: one half of the super-rows)
+#pragma unroll
+                      for (int t = 0; t < 2; ++t)
+                        {
+                          const long long G = Rj + t;
+                          tma_g2s_2d(dst + j * (2 * UB * 8) + t * (UB * 8), tm, ((int)(G & 1) * n1 + gx0 - K + shj) & ~1, (int)(G >> 1), bar);
+                        }
                     }
                 }
               if (owned)
                 {
-                  if (has_o0)
+#pragma unroll
+                  for (int t = 0; t < 2; ++t)
                     {
-                      tma_g2s_2d(dst + 2 * UB * 8, &a.tm_o0, (gx0 + a.sh_o0) & ~1, (int)((Ro + 1) >> 1), bar);
-                      tma_g2s_2d(dst + (2 * UB + OB) * 8, &a.tm_o0, (n1 + gx0 + a.sh_o0) & ~1, (int)(Ro >> 1), bar);
-                    }
-                  if (NOPS == 2)
-                    {
-                      tma_g2s_2d(dst + (2 * UB + 2 * OB) * 8, &a.tm_o1, (gx0 + a.sh_o1) & ~1, (int)((Ro + 1) >> 1), bar);
-                      tma_g2s_2d(dst + (2 * UB + 3 * OB) * 8, &a.tm_o1, (n1 + gx0 + a.sh_o1) & ~1, (int)(Ro >> 1), bar);
+                      const long long G = Ro + t; // operand rows of parity t
+                      if (has_o0)
+                        tma_g2s_2d(dst + (2 * UB + t * OB) * 8, &a.tm_o0, ((int)(G & 1) * n1 + gx0 + a.sh_o0) & ~1, (int)(G >> 1), bar);
+                      if (NOPS == 2)
+                        tma_g2s_2d(dst + (2 * UB + (2 + t) * OB) * 8, &a.tm_o1, ((int)(G & 1) * n1 + gx0 + a.sh_o1) & ~1, (int)(G >> 1), bar);
                     }
                 }
             }
         };
-        const int rb0_par = (int)(Rb0 & 1);
+        const int pb = a.pb[b];
 
         double acc[n][NPT]; // z-sums of the current layer: planes 0..K x the NPT owned nodes of this thread
 #pragma unroll
@@ -391,7 +412,6 @@ namespace spirk
 
         // running state of the plane loop (kept incrementally: no div / mod per step)
         unsigned slot = it0 % NBUF, phase = (it0 / NBUF) & 1; // ring slot of the plane and its mbarrier phase
-        int      par  = rb0_par;                             // parity of the staged row 0 of the plane (n1 is odd)
         int      P    = K * zf;                              // node plane
         int      sbuf = 0;                                   // a'/c tile buffer
         int      s    = 0;
@@ -401,21 +421,82 @@ namespace spirk
         // shared-memory offset of staged row r / operand row ro of a plane whose staged row 0 has parity par_: box of the
         // row's parity, position inside the box, and the 8-byte parity of the row start (a box starts at the 16-byte
         // aligned element at or below the first wanted one; gx0, K even, n1 odd)
+        // (the box is chosen by the parity of the STAGED row, so only the one-element alignment shift depends on the plane:
+        // a box must start at a 16-byte aligned global address - an odd FP64 start coordinate faults, tools/tma_test.cu)
         auto urow = [&](const int r, const int par_, const int sh = -1) {
-          const int blk = (par_ + r) & 1;
-          return blk * UB + ((r - (par_ ^ blk)) >> 1) * BW + ((sh < 0 ? a.sh_src : sh) ^ blk);
+          return (r & 1) * UB + (r >> 1) * BW + (((sh < 0 ? a.sh_src : sh) ^ par_ ^ r) & 1);
         };
         auto orow = [&](const int ro, const int par_, const int sh) {
-          const int blk = (par_ + ro) & 1; // K is even: operand row 0 (= staged row K) has the parity of staged row 0
-          return blk * OB + ((ro - (par_ ^ blk)) >> 1) * OW + (sh ^ blk);
+          // K is even: operand row 0 (= staged row K) has the parity of staged row 0
+          return (ro & 1) * OB + (ro >> 1) * OW + ((sh ^ par_ ^ ro) & 1);
         };
         // x-phase of the plane xP staged in ring slot xslot: a = Mx u, c = K'x u into the tile buffer xbuf
-        auto xphase = [&](const unsigned xslot, const unsigned xphase_bit, const int xpar, const int xP, const int xbuf) {
+        auto xphase = [&](const unsigned xslot, const unsigned xphase_bit, const int xpar, const int xP, const int xbuf,
+                          const int xzl = 1) {
           const bool    xzpl = (xP <= 0) || (xP >= n1 - 1);
           const double *xub  = RING + xslot * SLOT;
           double       *XA = AC + (NAC == 2 ? xbuf * (2 * LYS * PA) : 0), *XC = XA + LYS * PA;
           while (!mbar_try_wait(bar_u32 + 8 * xslot, xphase_bit))
             ;
+          if constexpr (MODE == V2_CHEB_FIRST)
+            {
+              // the first iterate x1 = f0 D^-1 b of the owned nodes of the plane is stored here, by the warps without an x task
+              constexpr int PRE0 = ((C::NXT + 31) / 32 * 32 < NT) ? (C::NXT + 31) / 32 * 32 : 0, NPRE = NT - PRE0;
+              const bool    xowned = (xzl > 0 || carry_in) && !xzpl && (xP >= K * L0) && (xP < K * L1);
+              if (xowned && wrp >= PRE0 / 32)
+                {
+                  const double *sdz = SD1 + (xzl % K) * (K * K);
+                  double       *d1p = const_cast<double *>(a.dinv) + boff + plane * (xP - a.zo0);
+                  constexpr int TOT = OY * (OX / 2);
+#pragma unroll
+                  for (int k = 0; k < (TOT + NPRE - 1) / NPRE; ++k)
+                    if (tid - PRE0 + k * NPRE < TOT)
+                      {
+                        const int     e = tid - PRE0 + k * NPRE;
+                        const int     ro = e / (OX / 2), x0 = (e % (OX / 2)) * 2;
+                        const double *pu = xub + urow(K + ro, xpar) + K + x0;
+                        const double *sd = sdz + (ro % K) * K + (x0 % K);
+                        const int     gx = gx0 + x0, gy = gy0 + ro;
+                        double       *dp = d1p + gx + (long long)n1 * gy;
+                        if (gy != 0)
+                          {
+                            if (gx != 0)
+                              dp[0] = sd[0] * pu[0];
+                            dp[1] = sd[1] * pu[1];
+                          }
+                      }
+                }
+            }
+          if constexpr (MODE == V2_CHEB_OWN)
+            {
+              // ---------------------------------------------------------- pointwise part of the Chebyshev epilogue,
+              // g = (rhs + ((1 + f1) x - f1 x_old) / (f2 dinv)) / sc for the owned nodes of the plane, written over the rhs
+              // operand in its ring slot, so that the y+z phase only subtracts g from its z-sums.  Done by warps that have
+              // no x task (the x-phase occupies NXT of the NT threads): thread = (x mod OX/2, row mod RG), nodes (x, x + OX/2)
+              // of the rows row + RG j - every node of a thread has the same node class (RG and OX/2 are multiples of K) and
+              // the same row parity, all offsets but one base per operand are compile-time.
+              constexpr int HX = OX / 2, PRE0 = ((C::NXT + 31) / 32 * 32 + 128 <= NT) ? (C::NXT + 31) / 32 * 32 : 0;
+              constexpr int RG = v3_pre_rows((NT - PRE0) / HX, OY, K); // rows handled side by side
+              static_assert(HX % K == 0 && RG > 0 && RG % K == 0 && RG % 2 == 0 && OY % RG == 0 && RG * HX <= NT - PRE0 && (RG * HX) % 32 == 0, "pre-pass thread layout");
+              const bool    xowned = (xzl > 0 || carry_in) && !xzpl && (xP >= K * L0) && (xP < K * L1);
+              if (xowned && wrp >= PRE0 / 32 && wrp < (PRE0 + RG * HX) / 32)
+                {
+                  const int     t_ = tid - PRE0, kx = t_ % HX, rs = t_ / HX; // rs < RG
+                  const double *pu = xub + urow(K + rs, xpar) + K + kx, *p0 = xub + 2 * UB + orow(rs, xpar, a.sh_o0) + kx;
+                  double       *p1 = RING + xslot * SLOT + 2 * UB + 2 * OB + orow(rs, xpar, a.sh_o1) + kx;
+                  const double  sd = SDI[(xzl % K) * (K * K) + (rs % K) * K + (kx % K)];
+#pragma unroll
+                  for (int j = 0; j < OY / RG; ++j)
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+                      {
+                        // rows rs + RG j: same box, RG / 2 box rows further on
+                        const int    ou = j * (RG / 2) * BW + t * HX, oo = j * (RG / 2) * OW + t * HX;
+                        const double x = pu[ou], xo = has_xo ? p0[oo] : 0.0;
+                        p1[oo]         = fma(fma(f1, x - xo, x), sd, sc_inv * p1[oo]);
+                      }
+                }
+            }
           // -------------------------------------------------------------- x-phase: a = Mx u, c = K'x u
           for (int q = tid; q < C::NXT; q += NT)
             {
@@ -591,6 +672,7 @@ namespace spirk
         // Lc = the layer the plane belongs to as plane ZL (for ZL == K: the layer it completes)
         auto step = [&](auto zl_c, const int Lc) {
           constexpr int ZL  = decltype(zl_c)::value;
+          const int     par = pb ^ (ZL & 1); // parity of the staged row 0 of this plane
           const bool    zpl = (P <= 0) || (P >= n1 - 1);
           const double *ub  = RING + slot * SLOT;
           const double *SA = AC + (NAC == 2 ? sbuf * (2 * LYS * PA) : 0), *SC = SA + LYS * PA;
@@ -606,8 +688,15 @@ namespace spirk
           else
             {
               if (NAC == 1)
-                __syncthreads(); // the a'/c tile of the previous plane is consumed
-              xphase(slot, phase, par, P, sbuf);
+                {
+                  // the a'/c tile of the previous plane is consumed: the warps that write it in the x-phase wait for all
+                  // readers, the others only announce that they are done (and start on the epilogue pre-pass)
+                  if (NT > (C::NXT + 31) / 32 * 32 && wrp >= (C::NXT + 31) / 32)
+                    asm volatile("bar.arrive 2, %0;" ::"r"(NT) : "memory");
+                  else
+                    asm volatile("bar.sync 2, %0;" ::"r"(NT) : "memory");
+                }
+              xphase(slot, phase, par, P, sbuf, ZL);
               __syncthreads();
               // the slot of the previous plane is free now (its operands were read in the previous y+z phase)
               if (s >= 1 && s - 1 + NBUF < nsteps)
@@ -616,6 +705,44 @@ namespace spirk
 
           if (is_yz)
             {
+              // -------------------------------------------------------------- linear part of the epilogue of this plane
+              // the z-sums run on (A x) / sc - g with  g = rhs / sc (residual) | (rhs + ((1 + f1) x - f1 x_old) / (f2 dinv)) / sc
+              // (Chebyshev); sc = the scalar factored out of the operator (see v3_apply)
+              const bool owned = (NOPS > 0 || CF) && (ZL > 0 || carry_in) && !zpl && (P >= K * L0) && (P < K * L1);
+              double     g[NPT];
+#pragma unroll
+              for (int i = 0; i < NPT; ++i)
+                g[i] = 0.0;
+              if (CF && owned)
+                {
+                  // b = src of this plane: g = kappa b (the first iterate x1 = f0 D^-1 b is stored during the x-phase)
+#pragma unroll
+                  for (int i = 0; i < NPT; ++i)
+                    g[i] = kappa * ub[urow(K + K * ys + i0 + i, par) + K + xl];
+                }
+              if (NOPS > 0 && owned)
+                {
+                  if (MODE == V2_RESIDUAL)
+                    {
+#pragma unroll
+                      for (int i = 0; i < NPT; ++i)
+                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i0 + i, par, a.sh_o0) + xl];
+                    }
+                  else
+                    {
+                      // formed during the x-phase (see xphase)
+#pragma unroll
+                      for (int i = 0; i < NPT; ++i)
+                        g[i] = ub[2 * UB + 2 * OB + orow(K * ys + i0 + i, par, a.sh_o1) + xl];
+                    }
+                }
+              // (subtracted BEFORE the y-sweep: g is dead while the sweep runs, and p / w go straight into the z-sums)
+              if ((NOPS > 0 || CF) && (ZL > 0 || carry_in))
+                {
+#pragma unroll
+                  for (int i = 0; i < NPT; ++i)
+                    acc[ZL][i] -= g[i];
+                }
               // -------------------------------------------------------------- y-sweep: p = My a, w = My c + K'y a
               double p[NPT], wv[NPT];
               {
@@ -693,50 +820,6 @@ namespace spirk
                         }
                     }
               }
-              // -------------------------------------------------------------- linear part of the epilogue of this plane
-              // the z-sums run on (A x) / sc - g with  g = rhs / sc (residual) | (rhs + ((1 + f1) x - f1 x_old) / (f2 dinv)) / sc
-              // (Chebyshev); sc = the scalar factored out of the operator (see v3_apply)
-              const bool owned = (NOPS > 0 || CF) && (ZL > 0 || carry_in) && !zpl && (P >= K * L0) && (P < K * L1);
-              double     g[NPT];
-#pragma unroll
-              for (int i = 0; i < NPT; ++i)
-                g[i] = 0.0;
-              if (CF && owned)
-                {
-                  // b = src of this plane: g = kappa b; the first iterate x1 = f0 D^-1 b is stored here, plane by plane
-                  const double   *sd1 = SD1 + ((ZL % K) * K + i0) * K + (xl % K);
-                  const int       gx = gx0 + xl, gyf = gy0 + K * ys + i0;
-                  double         *d1p = const_cast<double *>(a.dinv) + boff + gx + (long long)n1 * gyf + plane * (P - a.zo0);
-#pragma unroll
-                  for (int i = 0; i < NPT; ++i)
-                    {
-                      const double bi = ub[urow(K + K * ys + i0 + i, par) + K + xl];
-                      g[i]            = kappa * bi;
-                      if (gx != 0 && gyf + i != 0)
-                        d1p[i * n1] = sd1[i * K] * bi;
-                    }
-                }
-              if (NOPS > 0 && owned)
-                {
-                  if (MODE == V2_RESIDUAL)
-                    {
-#pragma unroll
-                      for (int i = 0; i < NPT; ++i)
-                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i0 + i, par, a.sh_o0) + xl];
-                    }
-                  else
-                    {
-                      const double *sdi = SDI + ((ZL % K) * K + i0) * K + (xl % K);
-#pragma unroll
-                      for (int i = 0; i < NPT; ++i)
-                        {
-                          const double x  = ub[urow(K + K * ys + i0 + i, par) + K + xl];
-                          const double xo = has_xo ? ub[2 * UB + orow(K * ys + i0 + i, par, a.sh_o0) + xl] : 0.0;
-                          const double rh = ub[2 * UB + 2 * OB + orow(K * ys + i0 + i, par, a.sh_o1) + xl];
-                          g[i]            = fma(fma(f1, x - xo, x), sdi[i * K], sc_inv * rh);
-                        }
-                    }
-                }
               // -------------------------------------------------------------- z-accumulation: out = Mz w + K'z p
               if constexpr (ZL < K)
                 {
@@ -745,12 +828,6 @@ namespace spirk
 #pragma unroll
                     for (int i = 0; i < NPT; ++i)
                       acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
-                  if ((NOPS > 0 || CF) && (ZL > 0 || carry_in))
-                    {
-#pragma unroll
-                      for (int i = 0; i < NPT; ++i)
-                        acc[ZL][i] -= g[i];
-                    }
                 }
               else
                 {
@@ -862,7 +939,7 @@ namespace spirk
 #pragma unroll
                   for (int i = 0; i < NPT; ++i)
                     {
-                      acc[0][i] = fma(MC(0, 0), wv[i], fma(KC(0, 0), p[i], acc[K][i])) - g[i];
+                      acc[0][i] = fma(MC(0, 0), wv[i], fma(KC(0, 0), p[i], acc[K][i]));
 #pragma unroll
                       for (int z = 1; z < n; ++z)
                         acc[z][i] = fma(MC(z, 0), wv[i], KC(z, 0) * p[i]);
@@ -890,15 +967,27 @@ namespace spirk
               if (s + NBUF < nsteps)
                 issue(s + NBUF);
             }
+#ifndef SPIRK_V3_NO_PIN
+          // pin the z-sums here: without it the compiler sinks the accumulation below the next barrier and spills p / w
+          // across it
+          if (is_yz)
+            {
+#pragma unroll
+              for (int z = 0; z < n; ++z)
+#pragma unroll
+                for (int i = 0; i < NPT; ++i)
+                  asm volatile("" : "+d"(acc[z][i]));
+            }
+#endif
           // advance the running state
-          ++s, ++P, par ^= 1, sbuf ^= 1;
+          ++s, ++P, sbuf ^= 1;
           if (++slot == NBUF)
             slot = 0, phase ^= 1;
         };
 
         if (C::PIPE)
           {
-            xphase(slot, phase, par, P, sbuf);
+            xphase(slot, phase, pb, P, sbuf);
             __syncthreads();
           }
         step(std::integral_constant<int, 0>{}, zf);
@@ -1011,6 +1100,8 @@ namespace spirk
     const long long below   = (long long)a.g.gh_lo * a.g.plane;
     const long long n_elems = (long long)(a.nb - 1) * a.stride + a.g.N + (long long)(a.g.gh_lo + a.g.gh_hi) * a.g.plane;
     a.L_lo = a.g.L_lo, a.L_hi = a.g.L_hi, a.zo0 = a.g.zo0, a.gh_lo = a.g.gh_lo;
+    for (int b = 0; b < a.nb && b < SPIRK_MAX_BLOCKS; ++b) // row index of a plane: b rows_per_block + n1 (P - zo0 + gh_lo) + gy0 - K
+      a.pb[b] = (int)(((long long)b * a.rows_per_block + a.gh_lo - a.zo0) & 1);
     if (int e = v3_make_map(&a.tm_src, &a.sh_src, a.src - below, n_elems, a.g.n1, C::BW, C::BH, l2p))
       return e;
     a.tm_o0 = a.tm_src, a.tm_o1 = a.tm_src, a.sh_o0 = a.sh_o1 = 0;

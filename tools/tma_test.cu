@@ -73,7 +73,9 @@ int main(int argc, char **argv)
   const long long Rb = (long long)n1 * 2 - 4;
   const int odd = argc > 3 ? atoi(argv[3]) : 0; // 0: even-row box, 1: odd-row box
   const int cw = (odd ? n1 : 0) - 4 + sh; // wanted first element
-  a.c0 = cw & ~1, a.c1 = odd ? (int)(Rb >> 1) : (int)((Rb + 1) >> 1), a.out = out;
+  const int exact = argc > 4 ? atoi(argv[4]) : 0; // 1: the box starts exactly at the wanted element (odd coordinates allowed?)
+  a.c0 = exact ? cw : (cw & ~1), a.c1 = odd ? (int)(Rb >> 1) : (int)((Rb + 1) >> 1), a.out = out;
+  printf("c0 = %d (exact %d)\n", a.c0, exact);
   k<BW, BH><<<1, 128, (BW * BH + 64) * 8 + 128>>>(a);
   cudaError_t e = cudaDeviceSynchronize();
   printf("kernel: %s\n", cudaGetErrorString(e));
