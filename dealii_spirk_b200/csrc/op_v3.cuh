@@ -40,7 +40,10 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdint>
+#include <functional>
+#include <vector>
 #include <type_traits>
 
 #include "op_v2.cuh"
@@ -162,6 +165,9 @@ namespace spirk
     // vertex plane through `carry` (whoever is ready first publishes, the other one adds and stores; a + b is commutative,
     // so the result is bitwise reproducible)
     int           dyn, n_items;
+    // the ranges of a column: n_big ranges of lock_len layers, then lock_nch - n_big ranges of len_small layers; all long
+    // items are drawn before the short ones, which fill the tail of the launch (items_big = nb * columns * n_big)
+    int           n_big, len_small, items_big;
     int          *sched;  // [0] next item, [1] CTAs that are done (the last one resets both)
     int          *state;  // per range boundary: 0 idle, 1 claimed by the first arrival, 2 its partial sums are published
     double       *carry;  // per range boundary: OX * OY partial sums
@@ -294,10 +300,21 @@ namespace spirk
                                                                  // indices and the per-block coefficients in uniform registers)
             if (item >= a.n_items)
               break;
-            col            = item % ncols;
-            const int rest = item / ncols, ch = rest % a.lock_nch;
-            b              = rest / a.lock_nch;
-            L0 = min(a.L_hi, a.L_lo + ch * a.lock_len), L1 = min(a.L_hi, a.L_lo + (ch + 1) * a.lock_len);
+            if (item < a.items_big)
+              {
+                col            = item % ncols;
+                const int rest = item / ncols, ch = rest % a.n_big;
+                b              = rest / a.n_big;
+                L0 = min(a.L_hi, a.L_lo + ch * a.lock_len), L1 = min(a.L_hi, L0 + a.lock_len);
+              }
+            else
+              {
+                const int it = item - a.items_big, n_small = a.lock_nch - a.n_big;
+                col            = it % ncols;
+                const int rest = it / ncols, ch = rest % n_small;
+                b              = rest / n_small;
+                L0 = min(a.L_hi, a.L_lo + a.n_big * a.lock_len + ch * a.len_small), L1 = min(a.L_hi, L0 + a.len_small);
+              }
           }
         else
           {
@@ -818,18 +835,20 @@ namespace spirk
                               p[ii] = pi, wv[ii] = wi + wk;
                             }
                         }
+                      // ------------------------------------------------------ z-accumulation: out = Mz w + K'z p
+                      // (inside the branch of this half: p / w do not have to be merged across the two branches, which the
+                      // register allocator did through the stack)
+                      if constexpr (ZL < K)
+                        {
+#pragma unroll
+                          for (int z = 0; z < n; ++z)
+#pragma unroll
+                            for (int i = 0; i < NPT; ++i)
+                              acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
+                        }
                     }
               }
-              // -------------------------------------------------------------- z-accumulation: out = Mz w + K'z p
-              if constexpr (ZL < K)
-                {
-#pragma unroll
-                  for (int z = 0; z < n; ++z)
-#pragma unroll
-                    for (int i = 0; i < NPT; ++i)
-                      acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
-                }
-              else
+              if constexpr (ZL == K)
                 {
 #pragma unroll
                   for (int z = 0; z < n; ++z)
@@ -861,7 +880,8 @@ namespace spirk
                       // layer below, the top plane of a range that ends below the top those of the layer above: the two CTAs
                       // meet at `state`; the first one publishes its partial sums, the second one adds them and stores.
                       auto combine = [&](const int Lb, const double(&part)[NPT]) {
-                        const int bnd = (b * ncols + col) * a.lock_nch + (Lb - a.L_lo) / a.lock_len;
+                        const int off = Lb - a.L_lo, nbl = a.n_big * a.lock_len; // index of the range that starts at layer Lb
+                        const int bnd = (b * ncols + col) * a.lock_nch + (off < nbl ? off / a.lock_len : a.n_big + (off - nbl) / a.len_small);
                         double   *cb  = a.carry + (size_t)bnd * (NY * NPT);
                         if (tid == 0)
                           QS[2] = atomicCAS(a.state + bnd, 0, 1);
@@ -1084,6 +1104,59 @@ namespace spirk
     return SPIRK_OK;
   }
 
+  // Ranges of a column for the work queue: n_big ranges of len_big layers followed by ranges of len_small layers.  The CTAs
+  // draw all long items first; the short ones fill the tail (with equal ranges the last round of a launch leaves most CTA
+  // slots idle: 1024 items on 296 slots = 3.46 rounds).  Chosen by simulating the queue (an item costs its layers + a fixed
+  // start-up of about 1.25 layers: pipeline fill, the recomputed / exchanged boundary plane).
+  inline void v3_plan_ranges(const long long cols, const int nloc, const long long slots, const int len_big, int &n_big, int &len_small)
+  {
+    struct Key
+    {
+      long long cols, slots;
+      int       nloc, len_big, n_big, len_small;
+    };
+    static thread_local std::vector<Key> cache;
+    for (const Key &k : cache)
+      if (k.cols == cols && k.slots == slots && k.nloc == nloc && k.len_big == len_big)
+        {
+          n_big = k.n_big, len_small = k.len_small;
+          return;
+        }
+    const double c0   = 1.25;
+    double       best = 1e300;
+    n_big = nloc / len_big, len_small = len_big;
+    std::vector<double> heap;
+    for (int nb_ = nloc / len_big; nb_ >= 0; --nb_)
+      for (int ls = len_big; ls >= 1; ls /= 2)
+        {
+          const int rem = nloc - nb_ * len_big;
+          if (rem <= 0 && ls != len_big)
+            continue;
+          const int ns = rem > 0 ? (rem + ls - 1) / ls : 0;
+          // the queue: every item goes to the slot that becomes free first
+          heap.assign((size_t)slots, 0.0);
+          auto run = [&](const long long count, const double cost) {
+            for (long long i = 0; i < count; ++i)
+              {
+                std::pop_heap(heap.begin(), heap.end(), std::greater<double>());
+                heap.back() += cost;
+                std::push_heap(heap.begin(), heap.end(), std::greater<double>());
+              }
+          };
+          run(cols * nb_, len_big + c0);
+          if (ns > 0)
+            {
+              run(cols * (ns - 1), ls + c0);
+              run(cols, (rem - (ns - 1) * ls) + c0);
+            }
+          const double t = *std::max_element(heap.begin(), heap.end());
+          if (t < best - 1e-9)
+            best = t, n_big = nb_, len_small = ls;
+        }
+    if (cache.size() < 64)
+      cache.push_back(Key{cols, slots, nloc, len_big, n_big, len_small});
+  }
+
   template <int K, int TX, int TY, int MODE, int NPT, int NBC = 1>
   int v3_launch_mode(spirk_ctx *ctx, V3Args &a)
   {
@@ -1122,6 +1195,7 @@ namespace spirk
     const long long slots = (long long)ctx->n_sms * C::MINB;
     long long       grid  = std::max(1LL, std::min(ctx->opt_v3_grid > 0 ? (long long)ctx->opt_v3_grid : slots, a.W / 4));
     a.lock_nch = 0, a.lock_len = 0, a.dyn = 0, a.n_items = 0, a.sched = nullptr, a.state = nullptr, a.carry = nullptr;
+    a.n_big = 0, a.len_small = 1, a.items_big = 0;
     const long long cols  = (long long)a.nb * a.ntx * a.nty;
     const int       nloc  = a.g.L_hi - a.g.L_lo; // cell layers of this slab
     const int       force = (a.g.col_size > 1) ? 2 : ctx->opt_v3_schedule; // (z-slabs: the work queue only)
@@ -1140,7 +1214,16 @@ namespace spirk
                 break;
               }
         len = std::max(1, std::min(len, nloc));
-        a.lock_len = len, a.lock_nch = (nloc + len - 1) / len;
+        a.lock_len = len, a.lock_nch = (nloc + len - 1) / len, a.n_big = a.lock_nch, a.len_small = len;
+        if (ctx->opt_v3_chunk <= 0 && ctx->opt_v3_tail != 0 && cols * a.lock_nch > slots)
+          {
+            // more items than CTA slots: long ranges first, short ones for the tail of the launch
+            int n_big, len_small;
+            v3_plan_ranges(cols, nloc, slots, len, n_big, len_small);
+            a.n_big = n_big, a.len_small = len_small;
+            a.lock_nch = n_big + (nloc - n_big * len + len_small - 1) / len_small;
+          }
+        a.items_big = (int)(cols * a.n_big);
         a.dyn      = 1;
         a.n_items  = (int)(cols * a.lock_nch);
         if (int e = ensure_v3_queue(ctx, (size_t)a.n_items, (size_t)a.n_items * C::NY * NPT))

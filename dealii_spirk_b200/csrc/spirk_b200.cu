@@ -364,6 +364,7 @@ int spirk_ctx_set_option(spirk_ctx *ctx, const char *name, int value)
                      {"v3_grid", &ctx->opt_v3_grid},               {"v3_smem_pad_kb", &ctx->opt_v3_smem_pad_kb},
                      {"v3_npt", &ctx->opt_v3_npt},                 {"v3_small_below", &ctx->opt_v3_small_below},
                      {"v3_l2promo", &ctx->opt_v3_l2promo},         {"v3_chunk", &ctx->opt_v3_chunk},
+                     {"v3_tail", &ctx->opt_v3_tail},
                      {"transfer_variant", &ctx->opt_transfer_variant}};
   for (const auto &t : table)
     if (std::strcmp(name, t.name) == 0)

@@ -102,6 +102,7 @@ def test_vector_kernels(gpu_dev):
     (5, 1, {"v3_schedule": 0}), (5, 1, {"v3_schedule": 1}), (5, 2, {"v3_schedule": 0, "v3_npt": 2}),
     (5, 2, {"v3_schedule": 1, "v3_npt": 4}), (5, 2, {}), (6, 2, {}), (6, 1, {"v3_schedule": 0}), (6, 2, {"v3_schedule": 1, "v3_npt": 2}),
     (5, 2, {"v3_small_below": 64}),  # 4 x 4-cell tiles at r = 5
+    (6, 2, {"v3_tail": 0}),  # equal ranges (the default at this size: long ranges first, short ones for the tail)
 ])
 def test_v3_all_modes_full_size(gpu_dev, r, nb, opts):
     ac.check_v3_full_size(gpu_dev, r, nb, opts)
