@@ -83,6 +83,10 @@ _SIGS = {
                            C.c_void_p, C.c_void_p, C.c_longlong, dp, dp],
     "spirk_op_cheb_first": [C.c_void_p, C.POINTER(Level), C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
                             dp, dp, dp],
+    "spirk_op_cheb_step_diag": [C.c_void_p, C.POINTER(Level), C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, dp, dp, C.c_longlong, dp, dp],
+    "spirk_op_cheb_first_diag": [C.c_void_p, C.POINTER(Level), C.POINTER(OpDesc), C.c_void_p, C.c_void_p, C.c_void_p, dp, dp,
+                                 C.c_longlong, dp, dp, dp],
     "spirk_op_inverse_diagonal": [C.c_void_p, C.POINTER(Level), C.c_void_p, C.c_double, C.c_double],
     "spirk_op_assemble_dense": [C.c_void_p, C.POINTER(Level), C.c_double, C.c_double, C.c_void_p],
     "spirk_mg_prolongate_add": [C.c_void_p, C.POINTER(Level), C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,

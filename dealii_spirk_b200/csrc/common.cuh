@@ -122,7 +122,8 @@ struct spirk_ctx
                                // 3 the round-1 heuristic (lockstep for vectors beyond the L2 capacity, else even split)
   int opt_v3_chunk       = 0;  // "v3_chunk": layers per work item (0 = 8)
   int opt_v3_tail        = 1;  // "v3_tail": 1 = long ranges first, short ranges for the tail of a launch (0 = equal ranges)
-  int opt_transfer_variant = 0; // "transfer_variant": 0 owner-computes 1-D sweeps, 1 cell-based kernels (restriction with atomics)
+  int opt_transfer_variant = 0; // "transfer_variant": 0 owner-computes 1-D sweeps (restriction z, y, x), 1 cell-based kernels (restriction
+                                // with atomics), 2 owner-computes sweeps with the restriction in the order x, y, z
   int opt_v3_grid        = 0;  // "v3_grid": 0 = all co-resident CTAs, > 0 = this many CTAs (even split)
   int opt_v3_smem_pad_kb = 0;  // "v3_smem_pad_kb": extra dynamic shared memory per CTA (limits the CTAs per SM; experiments)
   int opt_v3_npt         = 0;  // "v3_npt": nodes per y+z thread on 8 x 8 tiles, 0 = per mode (4 apply, 2 fused epilogues)

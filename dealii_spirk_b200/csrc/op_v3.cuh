@@ -77,7 +77,9 @@ namespace spirk
 #ifdef SPIRK_V3_NBUF
     static constexpr int NBUF = SPIRK_V3_NBUF;
 #else
-    static constexpr int NBUF = (NOPS == 0 && NBC == 1) ? 4 : 3; // ring depth (three / two planes in flight; 2 CTAs per SM must fit)
+    // ring depth (three / two planes in flight; 2 CTAs per SM must fit; coupled pairs stage the plane of both blocks, so
+    // with operand planes in the slot only one plane is in flight)
+    static constexpr int NBUF = (NBC > 1 && NOPS > 0) ? 2 : ((NOPS == 0 && NBC == 1) ? 4 : 3);
 #endif
 #ifdef SPIRK_V3_NAC
     static constexpr int NAC = SPIRK_V3_NAC;
@@ -90,9 +92,18 @@ namespace spirk
 #define SPIRK_V3_PIPE 0
 #endif
     static constexpr bool PIPE = (NAC == 2) && (SPIRK_V3_PIPE != 0);
+    // one code copy for the planes 1 .. K-1 of a cell layer (runtime plane position, z-coefficients from a shared-memory
+    // table) instead of K-1 specialised copies: the plane loop of the fused modes is 67 KB of SASS, twice the 32 KB
+    // instruction cache level (ncu: 1.65 "no instruction" stall cycles per issued instruction)
+#ifndef SPIRK_V3_MIDLOOP
+#define SPIRK_V3_MIDLOOP 0
+#endif
+    static constexpr bool MIDLOOP = (SPIRK_V3_MIDLOOP != 0) && (K >= 3);
+    static constexpr int  NZT = MIDLOOP ? 2 * (K + 1) * (K + 1) : 0; // {M(z, zl), K'(z, zl)} by plane position zl
     // coupled operators (NBC > 1 blocks, apply only): the x-phase mixes the mass sweeps of ALL blocks, so a ring slot
     // holds the staged plane of every block
-    static constexpr int SLOT = NBC * 2 * UB + NOPS * 2 * OB;
+    static constexpr int OPB  = NBC * 2 * UB; // the operand planes follow the staged planes in the ring slot
+    static constexpr int SLOT = OPB + NOPS * 2 * OB;
     static constexpr int NHALF = K / NPT;          // a cell segment in y is shared by NHALF threads of NPT nodes each
     static constexpr int NY   = OX * TY * NHALF; // y+z tasks (one thread each)
     static constexpr int NXT  = LYS * TX; // x-phase tasks
@@ -105,8 +116,8 @@ namespace spirk
     static constexpr int MINB = (NT > 256) ? 2 : (NT > 128 ? 3 : 6);
 #endif
     static constexpr unsigned BYTES_U = NBC * 2 * BW * BH * 8, BYTES_O = 2 * OB * 8;
-    static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 3 * K * K * K + NBUF + 2);
-    static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0 && NPT <= 4 && (NBC == 1 || NOPS == 0), "tile shape");
+    static constexpr size_t   smem = 128 + sizeof(double) * (size_t)(NBUF * SLOT + NAC * 2 * LYS * PA + 3 * K * K * K + NZT + NBUF + 2);
+    static_assert(NY % 32 == 0 && NT <= 1024 && K % NPT == 0 && NPT <= 4 && NBC <= 2, "tile shape");
     static constexpr int ISSUER = (NH > 0) ? NY : 0; // the thread that issues the TMA copies
     static_assert(UB % 16 == 0 && OB % 16 == 0 && OY % 2 == 0 && BW <= 256 && BH <= 256, "128-byte aligned TMA boxes");
   };
@@ -139,7 +150,11 @@ namespace spirk
           }
     return -1;
   }
-  constexpr int V3_NKP = 20; // distinct entries of K' per block (16 at k = 6) + the vertex diagonal in the last slot
+  constexpr int V3_F0C = 8;  // coupled pairs: f0 of block b sits in cc[V3_F0C + b]
+  constexpr int V3_NKP = 12; // distinct entries of K' per block (9 at k = 4, the only instantiated degree) + the vertex
+                             // diagonal in the last slot
+
+  static_assert(v3_cidx<4>(4, 4) < V3_NKP - 1 && v3_cidx<4>(2, 2) < V3_NKP - 1 && v3_cidx<4>(1, 3) < V3_NKP - 1, "compact coefficient list");
 
   struct V3Args
   {
@@ -149,11 +164,16 @@ namespace spirk
     double       *dst;
     const double *src, *x_old, *rhs, *dinv;
     double        cm[SPIRK_MAX_BLOCKS], cl[SPIRK_MAX_BLOCKS], f1[SPIRK_MAX_BLOCKS], f2[SPIRK_MAX_BLOCKS];
+    // fused Chebyshev modes: D = diagonal of dm M + dl K per node class (h-scaled).  The operator's own diagonal by
+    // default; the coefficients a stored inverse diagonal was computed with when the caller names them (the smoother
+    // of a level operator whose coefficients changed after the multigrid set-up)
+    double        dm[SPIRK_MAX_BLOCKS], dl[SPIRK_MAX_BLOCKS];
     // A = sc (Mz My K'x + Mz K'y Mx + K'z My Mx) with K' = Kh + cm / (3 cl) Mh, sc = cl  (cl = 0: K' = Mh / 3, sc = cm):
     // the mass term rides in the three stiffness terms, so no sweep scales its result
     double        sc[SPIRK_MAX_BLOCKS], kp[SPIRK_MAX_BLOCKS][V3_NKP];
     double        cc[16]; // coupled operators (<= 4 blocks): coupling * h^3, row-major; V2_CHEB_FIRST: f0 of the blocks
-                          // (x1 = f0 dinv src; x1 is written to the `dinv` pointer, which that mode does not read)
+                          // (x1 = f0 dinv src; x1 is written to the `dinv` pointer, which that mode does not read) - in
+                          // cc[b], for a coupled pair in cc[V3_F0C + b]
     int           coupled;
     int           km; // coupled pair whose second input is block b of ANOTHER vector (map tm_o0): dst_b = cl_b K u_b + cc[2b+1] M w_b
     int           ntx, nty;
@@ -241,11 +261,12 @@ namespace spirk
   {
     using C = CfgV3<K, TX, TY, MODE, NPT, NBC>;
     constexpr int n = C::n, OX = C::OX, OY = C::OY, LYS = C::LYS, BW = C::BW, UB = C::UB, OW = C::OW, OB = C::OB, PA = C::PA, NT = C::NT;
-    constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT, NY = C::NY, NH = C::NH;
+    constexpr int NOPS = C::NOPS, NBUF = C::NBUF, NAC = C::NAC, SLOT = C::SLOT, NY = C::NY, NH = C::NH, OPB = C::OPB;
     extern __shared__ __align__(16) double sm3_raw[];
     double   *sm3  = sm3_raw + (((128u - (smem_u32(sm3_raw) & 127u)) & 127u) >> 3); // TMA boxes: 128-byte aligned
     double   *RING = sm3, *AC = sm3 + NBUF * SLOT, *SDS = AC + NAC * 2 * LYS * PA, *SDI = SDS + K * K * K, *SD1 = SDI + K * K * K;
-    uint64_t *BAR  = reinterpret_cast<uint64_t *>(SD1 + K * K * K);
+    double   *ZT   = SD1 + K * K * K; // (MIDLOOP) z-coefficients by runtime plane position
+    uint64_t *BAR  = reinterpret_cast<uint64_t *>(ZT + C::NZT);
     int      *QS   = reinterpret_cast<int *>(BAR + NBUF); // [0] drawn item, [2] role at a range boundary
     const double *Mh = c_fe[K].Mh, *Kh = c_fe[K].Kh;
     const double  Mv = c_fe[K].Mv;
@@ -328,13 +349,15 @@ namespace spirk
           }
         const int       tx = col % a.ntx, ty = col / a.ntx;
         const int       gx0 = tx * OX, gy0 = ty * OY;
-        const double    cm = a.cm[b], cl = a.cl[b], f1 = a.f1[b], f2 = a.f2[b], sc = a.sc[b], sc_inv = 1.0 / sc;
+        const double    cl = a.cl[b], f1 = a.f1[b], f2 = a.f2[b], sc = a.sc[b], sc_inv = 1.0 / sc;
         const double   *kp = a.kp[b];
         constexpr bool  CF = (MODE == V2_CHEB_FIRST);
-        const double    f0 = CF ? a.cc[b] : 0.0, kappa = CF ? (1.0 + (1.0 + f1) * f0 / f2) * sc_inv : 0.0;
+        const double    f0 = CF ? a.cc[(NBC > 1 ? V3_F0C : 0) + b] : 0.0, kappa = CF ? (1.0 + (1.0 + f1) * f0 / f2) * sc_inv : 0.0;
         const double    Kv = kp[V3_NKP - 1];
         const long long boff = (long long)b * a.stride;
         const double   *src  = a.src + boff;
+        // coupled pair: the staged plane of the block this item produces inside a ring slot (km: plane 0 = u_b)
+        const int       bo   = (NBC > 1 && !a.km) ? b * (2 * UB) : 0;
         // range boundaries shared with another CTA of this launch (at the bottom of a z-slab the layer below is recomputed
         // from the ghost planes; the top plane of a slab belongs to the slab above)
         const bool      carry_in = a.dyn && L0 > a.L_lo, carry_out = a.dyn && L1 < a.L_hi;
@@ -345,6 +368,16 @@ namespace spirk
 
         if (!a.dyn)
           __syncthreads(); // the previous piece is finished with the ring, the a'/c tile and the tables
+        if (C::MIDLOOP && b != b_tab)
+          {
+            for (int e = tid; e < n * n; e += NT)
+              {
+                const int z = e / n, zl = e % n;
+                ZT[2 * (zl * n + z)] = Mh[v3_canon<K>(z, zl)], ZT[2 * (zl * n + z) + 1] = kp[v3_cidx<K>(z, zl)];
+              }
+            if (!(MODE == V2_CHEB_OWN || MODE == V2_CHEB_FIRST))
+              b_tab = b; // (read after the first barrier of the plane loop at the earliest)
+          }
         if ((MODE == V2_CHEB_OWN || MODE == V2_CHEB_FIRST) && b != b_tab)
           {
             // scaling by node class (position of the node inside its cell): -f2 / diag and its inverse
@@ -355,7 +388,7 @@ namespace spirk
                 const double mx = cx ? Mh[cx * n + cx] : Mv, kx = cx ? Kh[cx * n + cx] : Kv0;
                 const double my = cy ? Mh[cy * n + cy] : Mv, ky = cy ? Kh[cy * n + cy] : Kv0;
                 const double mz = cz ? Mh[cz * n + cz] : Mv, kz = cz ? Kh[cz * n + cz] : Kv0;
-                const double d  = cm * mx * my * mz + cl * (kx * my * mz + mx * ky * mz + mx * my * kz);
+                const double d  = a.dm[b] * mx * my * mz + a.dl[b] * (kx * my * mz + mx * ky * mz + mx * my * kz);
                 const double di = (fabs(d) > 1.0e-10) ? 1.0 / d : 1.0;
                 SDS[e] = -f2 * di * sc, SDI[e] = 1.0 / (f2 * di * sc), SD1[e] = f0 * di;
               }
@@ -408,9 +441,9 @@ namespace spirk
                     {
                       const long long G = Ro + t; // operand rows of parity t
                       if (has_o0)
-                        tma_g2s_2d(dst + (2 * UB + t * OB) * 8, &a.tm_o0, ((int)(G & 1) * n1 + gx0 + a.sh_o0) & ~1, (int)(G >> 1), bar);
+                        tma_g2s_2d(dst + (OPB + t * OB) * 8, &a.tm_o0, ((int)(G & 1) * n1 + gx0 + a.sh_o0) & ~1, (int)(G >> 1), bar);
                       if (NOPS == 2)
-                        tma_g2s_2d(dst + (2 * UB + (2 + t) * OB) * 8, &a.tm_o1, ((int)(G & 1) * n1 + gx0 + a.sh_o1) & ~1, (int)(G >> 1), bar);
+                        tma_g2s_2d(dst + (OPB + (2 + t) * OB) * 8, &a.tm_o1, ((int)(G & 1) * n1 + gx0 + a.sh_o1) & ~1, (int)(G >> 1), bar);
                     }
                 }
             }
@@ -471,7 +504,7 @@ namespace spirk
                       {
                         const int     e = tid - PRE0 + k * NPRE;
                         const int     ro = e / (OX / 2), x0 = (e % (OX / 2)) * 2;
-                        const double *pu = xub + urow(K + ro, xpar) + K + x0;
+                        const double *pu = xub + bo + urow(K + ro, xpar) + K + x0;
                         const double *sd = sdz + (ro % K) * K + (x0 % K);
                         const int     gx = gx0 + x0, gy = gy0 + ro;
                         double       *dp = d1p + gx + (long long)n1 * gy;
@@ -499,8 +532,8 @@ namespace spirk
               if (xowned && wrp >= PRE0 / 32 && wrp < (PRE0 + RG * HX) / 32)
                 {
                   const int     t_ = tid - PRE0, kx = t_ % HX, rs = t_ / HX; // rs < RG
-                  const double *pu = xub + urow(K + rs, xpar) + K + kx, *p0 = xub + 2 * UB + orow(rs, xpar, a.sh_o0) + kx;
-                  double       *p1 = RING + xslot * SLOT + 2 * UB + 2 * OB + orow(rs, xpar, a.sh_o1) + kx;
+                  const double *pu = xub + bo + urow(K + rs, xpar) + K + kx, *p0 = xub + OPB + orow(rs, xpar, a.sh_o0) + kx;
+                  double       *p1 = RING + xslot * SLOT + OPB + 2 * OB + orow(rs, xpar, a.sh_o1) + kx;
                   const double  sd = SDI[(xzl % K) * (K * K) + (rs % K) * K + (kx % K)];
 #pragma unroll
                   for (int j = 0; j < OY / RG; ++j)
@@ -612,10 +645,12 @@ namespace spirk
                         if (CF)
                           {
                             // first Chebyshev iterate x1 = f0 D^-1 b formed on the fly (node class = position in the cell)
+                            // (the blocks of a coupled pair share the diagonal, checked by v3_apply; block jb has its own f0)
                             const double *d1 = SD1 + ((((xP % K) + K) % K) * K + (row % K)) * K;
+                            const double  rj = (jb == b) ? 1.0 : a.cc[V3_F0C + jb] / f0;
 #pragma unroll
                             for (int j = 0; j < 2 * K + 1; ++j)
-                              u[j] *= d1[j % K];
+                              u[j] *= d1[j % K] * rj;
                           }
                         // mass sweep of this block; vertex row: two partial sums (short dependency chains)
                         double mj[K];
@@ -687,9 +722,12 @@ namespace spirk
 
         // one node plane; ZL = position of the plane in its cell layer (0 only for the first plane of a piece),
         // Lc = the layer the plane belongs to as plane ZL (for ZL == K: the layer it completes)
-        auto step = [&](auto zl_c, const int Lc) {
-          constexpr int ZL  = decltype(zl_c)::value;
-          const int     par = pb ^ (ZL & 1); // parity of the staged row 0 of this plane
+        auto step = [&](auto zl_c, const int Lc, const int zl_rt = 0) {
+          // ZLc < 0: one of the planes 1 .. K-1, position zl_rt at run time (MIDLOOP)
+          constexpr int  ZLc = decltype(zl_c)::value;
+          constexpr bool MID = (ZLc < 0);
+          const int      ZL  = MID ? zl_rt : ZLc;
+          const int      par = pb ^ (ZL & 1); // parity of the staged row 0 of this plane
           const bool    zpl = (P <= 0) || (P >= n1 - 1);
           const double *ub  = RING + slot * SLOT;
           const double *SA = AC + (NAC == 2 ? sbuf * (2 * LYS * PA) : 0), *SC = SA + LYS * PA;
@@ -735,7 +773,7 @@ namespace spirk
                   // b = src of this plane: g = kappa b (the first iterate x1 = f0 D^-1 b is stored during the x-phase)
 #pragma unroll
                   for (int i = 0; i < NPT; ++i)
-                    g[i] = kappa * ub[urow(K + K * ys + i0 + i, par) + K + xl];
+                    g[i] = kappa * ub[bo + urow(K + K * ys + i0 + i, par) + K + xl];
                 }
               if (NOPS > 0 && owned)
                 {
@@ -743,22 +781,36 @@ namespace spirk
                     {
 #pragma unroll
                       for (int i = 0; i < NPT; ++i)
-                        g[i] = sc_inv * ub[2 * UB + orow(K * ys + i0 + i, par, a.sh_o0) + xl];
+                        g[i] = sc_inv * ub[OPB + orow(K * ys + i0 + i, par, a.sh_o0) + xl];
                     }
                   else
                     {
                       // formed during the x-phase (see xphase)
 #pragma unroll
                       for (int i = 0; i < NPT; ++i)
-                        g[i] = ub[2 * UB + 2 * OB + orow(K * ys + i0 + i, par, a.sh_o1) + xl];
+                        g[i] = ub[OPB + 2 * OB + orow(K * ys + i0 + i, par, a.sh_o1) + xl];
                     }
                 }
               // (subtracted BEFORE the y-sweep: g is dead while the sweep runs, and p / w go straight into the z-sums)
-              if ((NOPS > 0 || CF) && (ZL > 0 || carry_in))
+              if constexpr (MID)
+                {
+                  if (NOPS > 0 || CF)
+                    {
+#pragma unroll
+                      for (int z = 1; z < K; ++z)
+                        if (ZL == z)
+                          {
+#pragma unroll
+                            for (int i = 0; i < NPT; ++i)
+                              acc[z][i] -= g[i];
+                          }
+                    }
+                }
+              else if ((NOPS > 0 || CF) && (ZLc > 0 || carry_in))
                 {
 #pragma unroll
                   for (int i = 0; i < NPT; ++i)
-                    acc[ZL][i] -= g[i];
+                    acc[ZLc < 0 ? 0 : ZLc][i] -= g[i];
                 }
               // -------------------------------------------------------------- y-sweep: p = My a, w = My c + K'y a
               double p[NPT], wv[NPT];
@@ -838,17 +890,29 @@ namespace spirk
                       // ------------------------------------------------------ z-accumulation: out = Mz w + K'z p
                       // (inside the branch of this half: p / w do not have to be merged across the two branches, which the
                       // register allocator did through the stack)
-                      if constexpr (ZL < K)
+                      if constexpr (MID)
+                        {
+                          const double2 *zt = reinterpret_cast<const double2 *>(ZT) + ZL * n;
+#pragma unroll
+                          for (int z = 0; z < n; ++z)
+                            {
+                              const double2 mk = zt[z];
+#pragma unroll
+                              for (int i = 0; i < NPT; ++i)
+                                acc[z][i] = fma(mk.x, wv[i], fma(mk.y, p[i], acc[z][i]));
+                            }
+                        }
+                      else if constexpr (ZLc < K)
                         {
 #pragma unroll
                           for (int z = 0; z < n; ++z)
 #pragma unroll
                             for (int i = 0; i < NPT; ++i)
-                              acc[z][i] = fma(MC(z, ZL), wv[i], fma(KC(z, ZL), p[i], acc[z][i]));
+                              acc[z][i] = fma(MC(z, (ZLc < 0 ? 0 : ZLc)), wv[i], fma(KC(z, (ZLc < 0 ? 0 : ZLc)), p[i], acc[z][i]));
                         }
                     }
               }
-              if constexpr (ZL == K)
+              if constexpr (ZLc == K)
                 {
 #pragma unroll
                   for (int z = 0; z < n; ++z)
@@ -966,7 +1030,7 @@ namespace spirk
                     }
                 }
             }
-          if ((NH > 0 ? !is_yz : true) && ZL == K && Lc >= L0)
+          if ((NH > 0 ? !is_yz : true) && ZLc == K && Lc >= L0)
             {
               // helpers (all threads without helper warps): Dirichlet faces x = n1-1 and y = n1-1 of the K planes of the
               // completed layer (owned by no tile)
@@ -1013,6 +1077,14 @@ namespace spirk
         step(std::integral_constant<int, 0>{}, zf);
         for (int Lc = zf; Lc < L1; ++Lc)
           {
+            if constexpr (C::MIDLOOP)
+              {
+#pragma unroll 1
+                for (int zl = 1; zl < K; ++zl)
+                  step(std::integral_constant<int, -1>{}, Lc, zl);
+                step(std::integral_constant<int, K>{}, Lc);
+                continue;
+              }
             step(std::integral_constant<int, 1>{}, Lc);
             if constexpr (K >= 2)
               step(std::integral_constant<int, (K >= 2 ? 2 : 1)>{}, Lc);
@@ -1257,24 +1329,42 @@ namespace spirk
   SPIRK_V3_EXTERN(V2_CHEB)
   SPIRK_V3_EXTERN(V2_CHEB_OWN)
   SPIRK_V3_EXTERN(V2_CHEB_FIRST)
-  extern template int v3_launch_mode<4, 8, 8, V2_APPLY, 4, 2>(spirk_ctx *, V3Args &);
-  extern template int v3_launch_mode<4, 4, 4, V2_APPLY, 4, 2>(spirk_ctx *, V3Args &);
+#undef SPIRK_V3_EXTERN
+#define SPIRK_V3_EXTERN(MODE)                                                                \
+  extern template int v3_launch_mode<4, 8, 8, MODE, 4, 2>(spirk_ctx *, V3Args &);           \
+  extern template int v3_launch_mode<4, 4, 4, MODE, 4, 2>(spirk_ctx *, V3Args &);
+  SPIRK_V3_EXTERN(V2_APPLY)
+  SPIRK_V3_EXTERN(V2_RESIDUAL)
+  SPIRK_V3_EXTERN(V2_CHEB)
+  SPIRK_V3_EXTERN(V2_CHEB_OWN)
+  SPIRK_V3_EXTERN(V2_CHEB_FIRST)
 #undef SPIRK_V3_EXTERN
   int v3_upload_constants_mode0(const FeConst *all);
   int v3_upload_constants_mode1(const FeConst *all);
   int v3_upload_constants_mode2(const FeConst *all);
   int v3_upload_constants_mode3(const FeConst *all);
   int v3_upload_constants_mode4(const FeConst *all);
+  int v3_upload_constants_mode5(const FeConst *all);
+  int v3_upload_constants_mode6(const FeConst *all);
 
   template <int K, int TX, int TY, int NPT>
   int v3_launch(spirk_ctx *ctx, V3Args &a, const V2Mode mode)
   {
     a.ntx = a.g.nc / TX, a.nty = a.g.nc / TY;
     a.W   = (long long)a.nb * a.ntx * a.nty * a.g.nc;
-    if (mode == V2_APPLY && a.coupled)
+    if (a.coupled)
       {
-        // coupled pair of blocks (IRK q = 2 system matrix, complex pair)
-        return v3_launch_mode<K, TX, TY, V2_APPLY, K, 2>(ctx, a);
+        // coupled pair of blocks (IRK q = 2 system matrix, complex pair); the fused epilogues serve the smoother and the
+        // residual of the complex level operators (operator.h:616-665 under preconditioner.h:353-373)
+        if (mode == V2_APPLY)
+          return v3_launch_mode<K, TX, TY, V2_APPLY, K, 2>(ctx, a);
+        if (mode == V2_RESIDUAL)
+          return v3_launch_mode<K, TX, TY, V2_RESIDUAL, K, 2>(ctx, a);
+        if (mode == V2_CHEB_FIRST)
+          return v3_launch_mode<K, TX, TY, V2_CHEB_FIRST, K, 2>(ctx, a);
+        if (a.dinv != nullptr)
+          return v3_launch_mode<K, TX, TY, V2_CHEB, K, 2>(ctx, a);
+        return v3_launch_mode<K, TX, TY, V2_CHEB_OWN, K, 2>(ctx, a);
       }
     if (mode == V2_APPLY)
       return v3_launch_mode<K, TX, TY, V2_APPLY, NPT>(ctx, a);
@@ -1290,19 +1380,28 @@ namespace spirk
   // returns SPIRK_ERR_UNSUPPORTED when the level / operator shape is not covered
   inline int v3_apply(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, V2Mode mode, double *dst, const double *src,
                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
-                      const double *f2, const double *f0 = nullptr, double *dst1 = nullptr)
+                      const double *f2, const double *f0 = nullptr, double *dst1 = nullptr, const double *diag_mass = nullptr,
+                      const double *diag_laplace = nullptr)
   {
     const bool coupled = (op->kind == SPIRK_OP_COUPLED);
     if (g.dim != 3 || g.k != 4 || g.nc % 4 != 0 || g.nc < 8)
       return SPIRK_ERR_UNSUPPORTED;
-    if (coupled && (mode != V2_APPLY || op->nb != 2))
-      return SPIRK_ERR_UNSUPPORTED; // coupled blocks: plain apply of a pair (the planes of both blocks are staged)
+    if (coupled && op->nb != 2)
+      return SPIRK_ERR_UNSUPPORTED; // coupled blocks: pairs only (the planes of both blocks are staged)
+    // fused first two Chebyshev iterates of a coupled pair: the first iterate of BOTH blocks is formed on the fly from one
+    // node-class table, so the blocks must share their diagonal (the complex pair does: operator.h:560-575)
+    {
+      const double m0 = diag_mass ? diag_mass[0] : op->coupling[0], m1 = diag_mass ? diag_mass[1] : op->coupling[3];
+      const double l0 = diag_laplace ? diag_laplace[0] : op->laplace[0], l1 = diag_laplace ? diag_laplace[1] : op->laplace[1];
+      if (coupled && mode == V2_CHEB_FIRST && (m0 != m1 || l0 != l1))
+        return SPIRK_ERR_UNSUPPORTED;
+    }
     if (op->nb > 1 && stride % g.n1 != 0)
       return SPIRK_ERR_UNSUPPORTED; // the blocks must continue the row sequence of block 0 (one tensor map)
     V3Args a;
     a.g = g, a.nb = op->nb, a.stride = stride, a.rows_per_block = stride / g.n1, a.coupled = coupled ? 1 : 0, a.km = 0;
     a.dst = dst, a.src = src, a.x_old = x_old, a.rhs = rhs, a.dinv = (mode == V2_CHEB_FIRST) ? dst1 : dinv;
-    if (mode == V2_CHEB_FIRST && (coupled || f0 == nullptr || dst1 == nullptr || dst1 == dst || dst1 == src))
+    if (mode == V2_CHEB_FIRST && (f0 == nullptr || dst1 == nullptr || dst1 == dst || dst1 == src))
       return SPIRK_ERR_UNSUPPORTED;
     const double hd = g.h * g.h * g.h, hl = g.h;
     constexpr int K = 4, n = K + 1;
@@ -1311,9 +1410,13 @@ namespace spirk
     for (int b = 0; b < op->nb; ++b)
       {
         a.cm[b] = coupled ? 0.0 : op->mass[b] * hd, a.cl[b] = op->laplace[b] * hl;
+        // node-class diagonal of the fused Chebyshev modes: block b's own term (coupled: coupling[b][b] M + laplace[b] K)
+        // unless the caller names the coefficients of the diagonal
+        a.dm[b] = (diag_mass ? diag_mass[b] : (coupled ? op->coupling[b * op->nb + b] : op->mass[b])) * hd;
+        a.dl[b] = (diag_laplace ? diag_laplace[b] : op->laplace[b]) * hl;
         a.f1[b] = f1 ? f1[b] : 0.0, a.f2[b] = f2 ? f2[b] : 0.0;
         if (mode == V2_CHEB_FIRST)
-          a.cc[b] = f0[b];
+          a.cc[(coupled ? V3_F0C : 0) + b] = f0[b];
         if (mode >= V2_CHEB && dinv == nullptr && a.f2[b] == 0.0)
           return SPIRK_ERR_UNSUPPORTED; // the folded Chebyshev epilogue divides by f2
         if (!coupled && a.cm[b] == 0.0 && a.cl[b] == 0.0)
@@ -1361,7 +1464,7 @@ namespace spirk
     fe_host_sym(K, Ms, Ks);
     for (int b = 0; b < nb; ++b)
       {
-        a.cm[b] = 0.0, a.cl[b] = laplace[b] * hl, a.f1[b] = a.f2[b] = 0.0, a.sc[b] = 1.0;
+        a.cm[b] = 0.0, a.cl[b] = laplace[b] * hl, a.f1[b] = a.f2[b] = 0.0, a.sc[b] = 1.0, a.dm[b] = a.dl[b] = 0.0;
         for (int i = 0; i < n; ++i)
           for (int j = 0; j < n; ++j)
             a.kp[b][v3_cidx<K>(i, j)] = Ks[i * n + j];

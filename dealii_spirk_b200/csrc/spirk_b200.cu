@@ -74,6 +74,10 @@ namespace spirk
       return e;
     if (int e = v3_upload_constants_mode4(all))
       return e;
+    if (int e = v3_upload_constants_mode5(all))
+      return e;
+    if (int e = v3_upload_constants_mode6(all))
+      return e;
     return SPIRK_OK;
   }
 
@@ -484,16 +488,18 @@ long long spirk_level_n_dofs(const spirk_level *lvl) { return make_geo(lvl).N; }
 // tile-column kernel (op_v2.cuh), 1 = general cell kernel only (op_v1.cuh)
 static int fast_apply(spirk_ctx *ctx, const Geo &g, const spirk_opdesc *op, V2Mode mode, double *dst, const double *src,
                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
-                      const double *f2)
+                      const double *f2, const double *diag_mass = nullptr, const double *diag_laplace = nullptr)
 {
   if (ctx->opt_apply_variant == 1)
     return SPIRK_ERR_UNSUPPORTED;
   if (ctx->opt_apply_variant == 0)
     {
-      int st = v3_apply(ctx, g, op, mode, dst, src, x_old, rhs, dinv, stride, f1, f2);
+      int st = v3_apply(ctx, g, op, mode, dst, src, x_old, rhs, dinv, stride, f1, f2, nullptr, nullptr, diag_mass, diag_laplace);
       if (st != SPIRK_ERR_UNSUPPORTED)
         return st;
     }
+  if (diag_mass || diag_laplace)
+    return SPIRK_ERR_UNSUPPORTED; // (the tile-column kernel only knows the operator's own diagonal)
   return v2_apply(ctx, g, op, mode, dst, src, x_old, rhs, dinv, stride, f1, f2);
 }
 // dst = A src into a scratch vector whose blocks sit at stride N: the fastest kernel that covers the operator
@@ -584,9 +590,13 @@ int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc
   return SPIRK_OK;
 }
 
-int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
-                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
-                       const double *f2)
+// mass factor of block b's own (diagonal) term
+static double own_mass(const spirk_opdesc *op, int b) { return op->kind == SPIRK_OP_REAL ? op->mass[b] : op->coupling[b * op->nb + b]; }
+
+// one Chebyshev iteration; dinv == NULL: the inverse diagonal of diag_mass[b] M + diag_laplace[b] K (NULL: of the operator)
+static int cheb_step_impl(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                          const double *x_old, const double *rhs, const double *dinv, const double *diag_mass,
+                          const double *diag_laplace, long long stride, const double *f1, const double *f2)
 {
   if (int e = check_level(lvl))
     return e;
@@ -596,22 +606,23 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
     return set_error(SPIRK_ERR_INVALID, "op_cheb_step: x_new must not alias x (it may alias x_old)");
   const Geo g = make_geo(lvl);
   {
-    int st = fast_apply(ctx, g, op, V2_CHEB, x_new, x, x_old, rhs, dinv, stride, f1, f2);
+    int st = fast_apply(ctx, g, op, V2_CHEB, x_new, x, x_old, rhs, dinv, stride, f1, f2, dinv ? nullptr : diag_mass,
+                        dinv ? nullptr : diag_laplace);
     if (st != SPIRK_ERR_UNSUPPORTED)
       return st;
   }
   // general path: A x into scratch, then the pointwise update; dinv == NULL -> the operator's own
-  // inverse diagonal (REAL operators only), materialised behind A x in the scratch buffer
+  // inverse diagonal (COUPLED: of block b's own term coupling[b][b] M + laplace[b] K), materialised behind A x in the
+  // scratch buffer
   const bool own_dinv = (dinv == nullptr);
-  if (own_dinv && op->kind != SPIRK_OP_REAL)
-    return set_error(SPIRK_ERR_INVALID, "op_cheb_step: dinv == NULL needs a REAL operator");
   if (int e = ensure_scratch(ctx, (size_t)g.N * op->nb * (own_dinv ? 2 : 1)))
     return e;
   if (own_dinv)
     {
       double *d = ctx->d_scratch + (size_t)g.N * op->nb;
       for (int b = 0; b < op->nb; ++b)
-        if (int e = spirk_op_inverse_diagonal(ctx, lvl, d + (size_t)b * g.N, op->mass[b], op->laplace[b]))
+        if (int e = spirk_op_inverse_diagonal(ctx, lvl, d + (size_t)b * g.N, diag_mass ? diag_mass[b] : own_mass(op, b),
+                                              diag_laplace ? diag_laplace[b] : op->laplace[b]))
           return e;
     }
   if (int e = apply_fast_or_any(ctx, g, op, ctx->d_scratch, x, stride, g.N))
@@ -626,39 +637,70 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
   return SPIRK_OK;
 }
 
+int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
+                       const double *f2)
+{
+  return cheb_step_impl(ctx, lvl, op, x_new, x, x_old, rhs, dinv, nullptr, nullptr, stride, f1, f2);
+}
+
+int spirk_op_cheb_step_diag(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                            const double *x_old, const double *rhs, const double *diag_mass, const double *diag_laplace,
+                            long long stride, const double *f1, const double *f2)
+{
+  if (!diag_mass || !diag_laplace)
+    return set_error(SPIRK_ERR_INVALID, "op_cheb_step_diag: the coefficients of the diagonal are required");
+  return cheb_step_impl(ctx, lvl, op, x_new, x, x_old, rhs, nullptr, diag_mass, diag_laplace, stride, f1, f2);
+}
+
 int spirk_op_fuses_own_diagonal(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op)
 {
-  if (!lvl || !op || op->kind != SPIRK_OP_REAL || ctx->opt_apply_variant != 0)
+  if (!lvl || !op || ctx->opt_apply_variant != 0 || (op->kind != SPIRK_OP_REAL && !(op->kind == SPIRK_OP_COUPLED && op->nb == 2)))
     return 0;
   const Geo g = make_geo(lvl);
   return (g.dim == 3 && g.k == 4 && g.nc % 4 == 0 && g.nc >= 8) ? 1 : 0; // the shapes v3_apply covers
 }
 
-int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
-                        long long stride, const double *f0, const double *f1, const double *f2)
+static int cheb_first_impl(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                           const double *diag_mass, const double *diag_laplace, long long stride, const double *f0, const double *f1,
+                           const double *f2)
 {
   if (int e = check_level(lvl))
     return e;
   if (int e = check_op(op))
     return e;
-  if (op->kind != SPIRK_OP_REAL)
-    return set_error(SPIRK_ERR_INVALID, "op_cheb_first: needs a REAL operator (its own inverse diagonal)");
   if (x1 == x2 || x1 == rhs || x2 == rhs)
     return set_error(SPIRK_ERR_INVALID, "op_cheb_first: x1, x2 and rhs must be distinct");
   const Geo g = make_geo(lvl);
   if (ctx->opt_apply_variant == 0)
     {
-      int st = v3_apply(ctx, g, op, V2_CHEB_FIRST, x2, rhs, nullptr, nullptr, nullptr, stride, f1, f2, f0, x1);
+      int st = v3_apply(ctx, g, op, V2_CHEB_FIRST, x2, rhs, nullptr, nullptr, nullptr, stride, f1, f2, f0, x1, diag_mass, diag_laplace);
       if (st != SPIRK_ERR_UNSUPPORTED)
         return st;
     }
   // general path: D^-1 into x2, x1 = f0 D^-1 rhs, then the ordinary Chebyshev step with x_old = 0
   for (int b = 0; b < op->nb; ++b)
-    if (int e = spirk_op_inverse_diagonal(ctx, lvl, x2 + (size_t)b * stride, op->mass[b], op->laplace[b]))
+    if (int e = spirk_op_inverse_diagonal(ctx, lvl, x2 + (size_t)b * stride, diag_mass ? diag_mass[b] : own_mass(op, b),
+                                          diag_laplace ? diag_laplace[b] : op->laplace[b]))
       return e;
   if (int e = spirk_vec_scale_pointwise(ctx, op->nb, g.N, x1, x2, rhs, stride, f0))
     return e;
-  return spirk_op_cheb_step(ctx, lvl, op, x2, x1, nullptr, rhs, nullptr, stride, f1, f2);
+  return cheb_step_impl(ctx, lvl, op, x2, x1, nullptr, rhs, nullptr, diag_mass, diag_laplace, stride, f1, f2);
+}
+
+int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                        long long stride, const double *f0, const double *f1, const double *f2)
+{
+  return cheb_first_impl(ctx, lvl, op, x1, x2, rhs, nullptr, nullptr, stride, f0, f1, f2);
+}
+
+int spirk_op_cheb_first_diag(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                             const double *diag_mass, const double *diag_laplace, long long stride, const double *f0, const double *f1,
+                             const double *f2)
+{
+  if (!diag_mass || !diag_laplace)
+    return set_error(SPIRK_ERR_INVALID, "op_cheb_first_diag: the coefficients of the diagonal are required");
+  return cheb_first_impl(ctx, lvl, op, x1, x2, rhs, diag_mass, diag_laplace, stride, f0, f1, f2);
 }
 
 int spirk_op_inverse_diagonal(spirk_ctx *ctx, const spirk_level *lvl, double *diag, double mass, double laplace)
@@ -852,7 +894,27 @@ int spirk_mg_restrict(spirk_ctx *ctx, const spirk_level *lf, int nb, double *coa
   };
   const dim3   blk_x(32, RPB);
   const size_t smem_x = sizeof(double) * ((size_t)RPB * (nf + ncn));
-  if (g.dim == 3)
+  if (g.dim == 3 && g.col_size == 1 && ctx->opt_transfer_variant != 2)
+    {
+      // whole mesh: z first, x last.  The sweeps along y / z run at the copy bandwidth (lanes along x, no staging), the x
+      // sweep at about a third of it (rows staged in shared memory): it gets the smallest array.  Measured at r = 6,
+      // nb = 2: x, y, z = 2 x 106 + 36 + 19 us; z, y, x: see profiles/README.md (`transfer_variant` 2 = the former order)
+      const Sweep1D wz = make_sweep(2, nf, nf, ncn, nf, ncc), wy = make_sweep(1, nf, ncn, ncn, nf, ncc);
+      if (int e = ensure_scratch(ctx, (size_t)nb * (wz.N_out + wy.N_out)))
+        return e;
+      double         *t1 = ctx->d_scratch, *t2 = ctx->d_scratch + (size_t)nb * wz.N_out;
+      const long long rpb = (long long)ncn * ncn, rows = rpb * nb;
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wz, ncc), 256, 0, ctx->stream>>>(wz, t1, wz.N_out, fine, fs)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      SPIRK_DISPATCH_K(g.k, (k_restrict_1d<K><<<grid_1d(wy, ncc), 256, 0, ctx->stream>>>(wy, t2, wy.N_out, t1, wz.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
+      if (smem_x > 48 * 1024)
+        SPIRK_DISPATCH_K(g.k, SPIRK_CUDA(cudaFuncSetAttribute(k_restrict_x<K, RPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_x)));
+      SPIRK_DISPATCH_K(g.k, (k_restrict_x<K, RPB><<<grid_for(ctx, (rows + RPB - 1) / RPB, 1, 16), blk_x, smem_x, ctx->stream>>>(
+                              nf, ncc, rows, rpb, coarse, cs, t2, wy.N_out)));
+      SPIRK_LAUNCH_CHECK(ctx);
+    }
+  else if (g.dim == 3)
     {
       const int       zin = g.gh_lo + t.zf_owned + g.gh_hi; // fine planes in memory per block
       const Sweep1D   wx = make_sweep(0, ncn, nf, zin, nf, ncc), wy = make_sweep(1, ncn, ncn, zin, nf, ncc);

@@ -193,9 +193,9 @@ namespace spirk_host
         const spirk_opdesc op = opdesc(l);
         // the kernel forms D^-1 on the fly only where that is fused into the cell pass (elsewhere it would be recomputed
         // into scratch memory on every call: pass the stored diagonal)
-        bool own_dinv = op.kind == SPIRK_OP_REAL && (int)L.dinv_mass.size() == nb && spirk_op_fuses_own_diagonal(dev->ctx(), &L.level, &op);
-        for (int i = 0; own_dinv && i < nb; ++i)
-          own_dinv = L.dinv_mass[i] == op.mass[i] && L.dinv_laplace[i] == op.laplace[i];
+        // (the stored inverse diagonal is the diagonal of dinv_mass[i] M + dinv_laplace[i] K, the operator's coefficients at
+        // reinit(); the kernel forms exactly that per node class, whatever the live coefficients are - SURVEY 2.4(9))
+        const bool own_dinv = (int)L.dinv_mass.size() == nb && spirk_op_fuses_own_diagonal(dev->ctx(), &L.level, &op);
         std::vector<double> rhok(nb), sigma(nb);
         bool                any = false;
         for (int i = 0; i < nb; ++i)
@@ -224,13 +224,18 @@ namespace spirk_host
             if (k == 0 && fuse_first)
               {
                 L.mf.exchange_ghosts(const_cast<double *>(b.data()), nb, L.stride, kd, 1);
-                SPIRK_CHECK(spirk_op_cheb_first(dev->ctx(), &L.level, &op, cur, old, b.data(), L.stride, f.data(), f1.data(), f2.data()));
+                SPIRK_CHECK(spirk_op_cheb_first_diag(dev->ctx(), &L.level, &op, cur, old, b.data(), L.dinv_mass.data(),
+                                                     L.dinv_laplace.data(), L.stride, f.data(), f1.data(), f2.data()));
               }
             else
               {
                 L.mf.exchange_ghosts(cur, nb, L.stride, kd, 1);
-                SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
-                                               own_dinv ? nullptr : L.dinv.data(), L.stride, f1.data(), f2.data()));
+                if (own_dinv)
+                  SPIRK_CHECK(spirk_op_cheb_step_diag(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
+                                                      L.dinv_mass.data(), L.dinv_laplace.data(), L.stride, f1.data(), f2.data()));
+                else
+                  SPIRK_CHECK(spirk_op_cheb_step(dev->ctx(), &L.level, &op, old, cur, k == 0 ? nullptr : old, b.data(),
+                                                 L.dinv.data(), L.stride, f1.data(), f2.data()));
               }
             std::swap(cur, old);
           }
@@ -427,6 +432,14 @@ namespace spirk_host
           if (d.kind == SPIRK_OP_REAL)
             {
               L.dinv_mass.assign(d.mass, d.mass + d.nb);
+              L.dinv_laplace.assign(d.laplace, d.laplace + d.nb);
+            }
+          else if (d.nb == 2 && d.coupling[0] == d.coupling[3] && d.laplace[0] == d.laplace[1])
+            {
+              // complex pair: compute_inverse_diagonal is the diagonal of lambda_re M + tau K in both blocks
+              // (operator.h:560-575) = the diagonal of each block's own term; remembered so that the smoother can let the
+              // kernel form it on the fly while the live coefficients still equal the ones of this set-up
+              L.dinv_mass.assign({d.coupling[0], d.coupling[3]});
               L.dinv_laplace.assign(d.laplace, d.laplace + d.nb);
             }
         }

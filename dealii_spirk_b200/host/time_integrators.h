@@ -505,7 +505,10 @@ namespace spirk_host
         {
           const double t0 = now_ns(src);
           const auto  &mf = p.op_level();
-          if (p.row.size == 1)
+          // all stages on this rank: one cell pass with the coupled descriptor - where the device library has a
+          // plane-streaming kernel for it (pairs); for more stages the mixing + one K v + M w pass below is the fast form
+          // (the general cell kernel with atomics is the only one that covers coupled operators of more than two blocks)
+          if (p.row.size == 1 && (p.n_stages <= 2 || !mix_then_km()))
             {
               spirk_opdesc d;
               std::memset(&d, 0, sizeof(d));
@@ -532,6 +535,16 @@ namespace spirk_host
                                             src.stride(), tau.data(), one.data()));
             }
           p.time_system_vmult += now_ns(src) - t0;
+        }
+        static bool mix_then_km()
+        {
+          static int v = -1;
+          if (v < 0)
+            {
+              const char *e = std::getenv("SPIRK_IRK_COUPLED_PASS"); // 1: the coupled cell pass for any number of stages
+              v             = (e && std::atoi(e) == 1) ? 0 : 1;
+            }
+          return v == 1;
         }
       };
 

@@ -132,19 +132,31 @@ int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc
                       const double *rhs, const double *src, long long stride);
 /* one Chebyshev iteration (deal.II PreconditionChebyshev, preconditioner.h:353-373):
  *   x_new = x + f1[b] (x - x_old) + f2[b] dinv .* (rhs - A x);  x_old == NULL means x_old = 0;
- *   dinv == NULL means "the inverse diagonal of op itself" (spirk_op_inverse_diagonal with op's
- *   coefficients; REAL operators only) and saves reading that vector; x_new may alias x_old, not x */
+ *   dinv == NULL means "the inverse diagonal of op itself" (spirk_op_inverse_diagonal with op's coefficients; COUPLED:
+ *   of block b's own term coupling[b][b] M + laplace[b] K, what ComplexMassLaplaceOperator::compute_inverse_diagonal
+ *   returns, operator.h:560-575) and saves reading that vector; x_new may alias x_old, not x */
 int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op,
                        double *x_new, const double *x, const double *x_old, const double *rhs,
                        const double *dinv, long long stride, const double *f1, const double *f2);
 /* 1 if spirk_op_cheb_step / spirk_op_cheb_first with dinv == NULL run on a fused kernel that forms the inverse diagonal on
  * the fly for this level and operator; 0 if they would materialise it on every call (pass the stored vector then) */
 int spirk_op_fuses_own_diagonal(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op);
+/* The same Chebyshev iteration with dinv = the inverse diagonal of diag_mass[b] M + diag_laplace[b] K, formed on the fly:
+ * the smoother of a level operator whose coefficients were changed after the multigrid set-up (the stored inverse diagonal
+ * of PreconditionerGMG stems from the coefficients at reinit(), preconditioner.h:343-373; the complex batched schemes set
+ * it up with the constructor defaults).  32 B per DoF where spirk_op_fuses_own_diagonal() == 1. */
+int spirk_op_cheb_step_diag(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                            const double *x_old, const double *rhs, const double *diag_mass, const double *diag_laplace,
+                            long long stride, const double *f1, const double *f2);
 /* the first two Chebyshev iterates from a zero start in one pass over rhs (PreconditionChebyshev::vmult, iteration 0
  * and 1): x1 = f0[b] dinv .* rhs;  x2 = x1 + f1[b] x1 + f2[b] dinv .* (rhs - A x1), dinv = the inverse diagonal of op
  * itself (REAL operators).  24 B per DoF instead of 48 for spirk_vec_scale_pointwise + spirk_op_cheb_step. */
 int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2,
                         const double *rhs, long long stride, const double *f0, const double *f1, const double *f2);
+/* ... with dinv = the inverse diagonal of diag_mass[b] M + diag_laplace[b] K (see spirk_op_cheb_step_diag) */
+int spirk_op_cheb_first_diag(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2,
+                             const double *rhs, const double *diag_mass, const double *diag_laplace, long long stride,
+                             const double *f0, const double *f1, const double *f2);
 /* inverse diagonal of mass*M + laplace*K: abs(d) > 1e-10 ? 1/d : 1, Dirichlet entries 1
  * (operator.h:361-373, 560-575, 775-792) */
 int spirk_op_inverse_diagonal(spirk_ctx *ctx, const spirk_level *lvl, double *diag, double mass,

@@ -788,9 +788,9 @@ int spirk_op_residual(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc
   return SPIRK_OK;
 }
 
-int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
-                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
-                       const double *f2)
+static int cheb_step_impl(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                          const double *x_old, const double *rhs, const double *dinv, const double *diag_mass,
+                          const double *diag_laplace, long long stride, const double *f1, const double *f2)
 {
   const long long N = Geo(lvl).N;
   ctx->scratch.resize((size_t)op->nb * N);
@@ -799,11 +799,12 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
   std::vector<double> own; // dinv == NULL: the operator's own inverse diagonal
   if (!dinv)
     {
-      if (op->kind != SPIRK_OP_REAL)
-        return fail(SPIRK_ERR_INVALID, "cheb_step: dinv == NULL needs a REAL operator");
+      // (COUPLED: the diagonal of block b's own term, coupling[b][b] M + laplace[b] K)
       own.resize((size_t)op->nb * stride);
       for (int b = 0; b < op->nb; ++b)
-        spirk_op_inverse_diagonal(ctx, lvl, own.data() + b * stride, op->mass[b], op->laplace[b]);
+        spirk_op_inverse_diagonal(ctx, lvl, own.data() + b * stride,
+                                  diag_mass ? diag_mass[b] : (op->kind == SPIRK_OP_REAL ? op->mass[b] : op->coupling[b * op->nb + b]),
+                                  diag_laplace ? diag_laplace[b] : op->laplace[b]);
       dinv = own.data();
     }
   for (int b = 0; b < op->nb; ++b)
@@ -823,20 +824,52 @@ int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdes
 }
 
 // first two Chebyshev iterates from a zero start: x1 = f0 dinv rhs, x2 = x1 + f1 x1 + f2 dinv (rhs - A x1)
-int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
-                        long long stride, const double *f0, const double *f1, const double *f2)
+int spirk_op_cheb_step(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                       const double *x_old, const double *rhs, const double *dinv, long long stride, const double *f1,
+                       const double *f2)
 {
-  if (op->kind != SPIRK_OP_REAL)
-    return fail(SPIRK_ERR_INVALID, "cheb_first: needs a REAL operator");
+  return cheb_step_impl(ctx, lvl, op, x_new, x, x_old, rhs, dinv, nullptr, nullptr, stride, f1, f2);
+}
+
+int spirk_op_cheb_step_diag(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x_new, const double *x,
+                            const double *x_old, const double *rhs, const double *diag_mass, const double *diag_laplace,
+                            long long stride, const double *f1, const double *f2)
+{
+  if (!diag_mass || !diag_laplace)
+    return fail(SPIRK_ERR_INVALID, "cheb_step_diag: the coefficients of the diagonal are required");
+  return cheb_step_impl(ctx, lvl, op, x_new, x, x_old, rhs, nullptr, diag_mass, diag_laplace, stride, f1, f2);
+}
+
+static int cheb_first_impl(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                           const double *diag_mass, const double *diag_laplace, long long stride, const double *f0, const double *f1,
+                           const double *f2)
+{
   const long long N = Geo(lvl).N;
   for (int b = 0; b < op->nb; ++b)
     {
-      if (int e = spirk_op_inverse_diagonal(ctx, lvl, x2 + b * stride, op->mass[b], op->laplace[b]))
+      if (int e = spirk_op_inverse_diagonal(ctx, lvl, x2 + b * stride,
+                                            diag_mass ? diag_mass[b] : (op->kind == SPIRK_OP_REAL ? op->mass[b] : op->coupling[b * op->nb + b]),
+                                            diag_laplace ? diag_laplace[b] : op->laplace[b]))
         return e;
       for (long long i = 0; i < N; ++i)
         x1[b * stride + i] = f0[b] * x2[b * stride + i] * rhs[b * stride + i];
     }
-  return spirk_op_cheb_step(ctx, lvl, op, x2, x1, nullptr, rhs, nullptr, stride, f1, f2);
+  return cheb_step_impl(ctx, lvl, op, x2, x1, nullptr, rhs, nullptr, diag_mass, diag_laplace, stride, f1, f2);
+}
+
+int spirk_op_cheb_first(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                        long long stride, const double *f0, const double *f1, const double *f2)
+{
+  return cheb_first_impl(ctx, lvl, op, x1, x2, rhs, nullptr, nullptr, stride, f0, f1, f2);
+}
+
+int spirk_op_cheb_first_diag(spirk_ctx *ctx, const spirk_level *lvl, const spirk_opdesc *op, double *x1, double *x2, const double *rhs,
+                             const double *diag_mass, const double *diag_laplace, long long stride, const double *f0, const double *f1,
+                             const double *f2)
+{
+  if (!diag_mass || !diag_laplace)
+    return fail(SPIRK_ERR_INVALID, "cheb_first_diag: the coefficients of the diagonal are required");
+  return cheb_first_impl(ctx, lvl, op, x1, x2, rhs, diag_mass, diag_laplace, stride, f0, f1, f2);
 }
 
 int spirk_op_inverse_diagonal(spirk_ctx *, const spirk_level *lvl, double *diag, double mass, double laplace)

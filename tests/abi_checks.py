@@ -154,6 +154,78 @@ def check_residual_and_cheb(dev, dim, k, r, nb=2):
         assert relerr(ctx.download(dxo, x.shape), ref) < RTOL
 
 
+
+def check_coupled_fused(dev, dim, k, r, desc=None, opts=None, tol=RTOL):
+    """Residual and Chebyshev steps of a COUPLED pair of blocks (the complex level operator, reference operator.h:616-665,
+    under the smoother of preconditioner.h:353-373): explicit inverse diagonal, the operator's own diagonal (dinv == NULL:
+    the diagonal of block b's own term coupling[b][b] M + laplace[b] K), x_old = 0, x_new aliasing x_old, and the fused
+    first two iterations; against the Kronecker oracle."""
+    desc = desc or OP_CASES[4]
+    lvl, olv = make_level(dim, k, r)
+    Cm = np.asarray(desc[1], float)
+    nb = Cm.shape[0]
+    lap = np.broadcast_to(np.atleast_1d(np.asarray(desc[2], float)), (nb,)).copy()
+    op = capi.coupled_op(Cm, lap)
+
+    def apply(u):
+        v = u.copy()
+        v[:, olv.bmask] = 0.0
+        out = olv.apply(v, 0.0, lap) + np.tensordot(Cm, olv.apply(v, 1.0, 0.0), axes=(1, 0))
+        out[:, olv.bmask] = u[:, olv.bmask]
+        return out
+
+    x, xo, b = block_input(olv, nb, 3, True), block_input(olv, nb, 4, True), block_input(olv, nb, 5, True)
+    bb = block_input(olv, nb, 6, False)
+    own = np.concatenate([olv.inverse_diagonal(Cm[i, i], lap[i]) for i in range(nb)])
+    other = np.concatenate([olv.inverse_diagonal(1.0 + i, 1.0) for i in range(nb)])  # a diagonal that is NOT the operator's
+    f0, f1, f2 = np.array([0.7, 0.6][:nb]), np.array([0.3, 0.2][:nb]), np.array([1.1, 0.9][:nb])
+    bc = (slice(None),) + (None,) * dim
+    Ax = apply(x)
+    errs = {}
+    with capi.Context(dev) as ctx:
+        set_options(ctx, opts)
+        dx, dxo, db, dbb, dd = (ctx.upload(a) for a in (x, xo, b, bb, other))
+        d1, d2 = ctx.alloc(x.size), ctx.alloc(x.size)
+        pf0, _0 = capi.darr(f0)
+        pf1, _1 = capi.darr(f1)
+        pf2, _2 = capi.darr(f2)
+        N, shape = olv.N, x.shape
+        ctx.call("spirk_op_residual", C.byref(lvl), C.byref(op), d1, db, dx, N)
+        errs["residual"] = relerr(ctx.download(d1, shape), b - Ax)
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), d1, dx, dxo, db, dd, N, pf1, pf2)
+        errs["cheb_dinv"] = relerr(ctx.download(d1, shape), x + f1[bc] * (x - xo) + f2[bc] * other.reshape(shape) * (b - Ax))
+        ref = x + f1[bc] * (x - xo) + f2[bc] * own.reshape(shape) * (b - Ax)
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), d1, dx, dxo, db, None, N, pf1, pf2)
+        errs["cheb_own"] = relerr(ctx.download(d1, shape), ref)
+        if dim == 3 and k == 4 and r >= 3 and not (opts or {}).get("apply_variant"):  # (the general cell kernel uses atomics)
+            ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), d2, dx, dxo, db, None, N, pf1, pf2)
+            assert np.array_equal(ctx.download(d1, shape), ctx.download(d2, shape)), "bitwise reproducible"
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), d1, dx, None, db, None, N, pf1, pf2)
+        errs["cheb_own_x0"] = relerr(ctx.download(d1, shape), (1 + f1[bc]) * x + f2[bc] * own.reshape(shape) * (b - Ax))
+        ctx.call("spirk_op_cheb_first", C.byref(lvl), C.byref(op), d1, d2, dbb, N, pf0, pf1, pf2)
+        x1 = f0[bc] * own.reshape(shape) * bb
+        x2 = x1 + f1[bc] * x1 + f2[bc] * own.reshape(shape) * (bb - apply(x1))
+        errs["cheb_first_x1"] = relerr(ctx.download(d1, shape), x1)
+        errs["cheb_first_x2"] = relerr(ctx.download(d2, shape), x2)
+        # the diagonal of OTHER coefficients, formed on the fly (a smoother set up before the operator's coefficients changed)
+        pdm, _3 = capi.darr([1.0 + i for i in range(nb)])
+        pdl, _4 = capi.darr([1.0] * nb)
+        ctx.call("spirk_op_cheb_step_diag", C.byref(lvl), C.byref(op), d1, dx, dxo, db, pdm, pdl, N, pf1, pf2)
+        errs["cheb_diag"] = relerr(ctx.download(d1, shape), x + f1[bc] * (x - xo) + f2[bc] * other.reshape(shape) * (b - Ax))
+        o2 = np.concatenate([olv.inverse_diagonal(1.5, 0.7)] * nb).reshape(shape)
+        pdm2, _5 = capi.darr([1.5] * nb)
+        pdl2, _6 = capi.darr([0.7] * nb)
+        ctx.call("spirk_op_cheb_first_diag", C.byref(lvl), C.byref(op), d1, d2, dbb, pdm2, pdl2, N, pf0, pf1, pf2)
+        y1 = f0[bc] * o2 * bb
+        errs["cheb_first_diag_x1"] = relerr(ctx.download(d1, shape), y1)
+        errs["cheb_first_diag_x2"] = relerr(ctx.download(d2, shape), y1 + f1[bc] * y1 + f2[bc] * o2 * (bb - apply(y1)))
+        ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dxo, dx, dxo, db, None, N, pf1, pf2)  # x_new aliases x_old
+        errs["cheb_own_alias"] = relerr(ctx.download(dxo, shape), ref)
+    bad = {k_: v for k_, v in errs.items() if not v < tol}
+    assert not bad, f"coupled fused dim={dim} k={k} r={r} opts={opts}: {bad}"
+    return errs
+
+
 _FULL_CACHE = {}
 
 
@@ -174,7 +246,12 @@ def full_size_case(r, nb):
         Ax = olv.apply(x, mass, lap)
         x1 = f0[bc] * dinv * bb
         x2 = x1 + f1[bc] * x1 + f2[bc] * dinv * (bb - olv.apply(x1, mass, lap))
+        dm, dl = 1.3 * mass + 0.2, np.full(nb, 0.25)
+        dinv2 = np.concatenate([olv.inverse_diagonal(m, 0.25) for m in dm]).reshape(x.shape)
+        y1 = f0[bc] * dinv2 * bb
+        y2 = y1 + f1[bc] * y1 + f2[bc] * dinv2 * (bb - olv.apply(y1, mass, lap))
         _FULL_CACHE[key] = dict(olv=olv, mass=mass, lap=lap, x=x, xo=xo, b=b, bb=bb, dinv=dinv, f0=f0, f1=f1, f2=f2, Ax=Ax,
+                                dm=dm, dl=dl, y1=y1, y2=y2, cheb_diag=x + f1[bc] * (x - xo) + f2[bc] * dinv2 * (b - Ax),
                                 res=b - Ax, cheb=x + f1[bc] * (x - xo) + f2[bc] * dinv * (b - Ax),
                                 cheb0=(1 + f1[bc]) * x + f2[bc] * dinv * (b - Ax), x1=x1, x2=x2)
     return _FULL_CACHE[key]
@@ -212,6 +289,14 @@ def check_v3_full_size(dev, r, nb, opts=None, tol=RTOL):
         ctx.call("spirk_op_cheb_first", C.byref(lvl), C.byref(op), d1, d2, dbb, N, pf0, pf1, pf2)
         errs["cheb_first_x1"] = relerr(ctx.download(d1, shape), c["x1"])
         errs["cheb_first_x2"] = relerr(ctx.download(d2, shape), c["x2"])
+        # the diagonal of other coefficients than the operator's, formed on the fly (spirk_op_cheb_step_diag / _first_diag)
+        pdm, _3 = capi.darr(c["dm"])
+        pdl, _4 = capi.darr(c["dl"])
+        ctx.call("spirk_op_cheb_step_diag", C.byref(lvl), C.byref(op), d1, dx, dxo, db, pdm, pdl, N, pf1, pf2)
+        errs["cheb_diag"] = relerr(ctx.download(d1, shape), c["cheb_diag"])
+        ctx.call("spirk_op_cheb_first_diag", C.byref(lvl), C.byref(op), d1, d2, dbb, pdm, pdl, N, pf0, pf1, pf2)
+        errs["cheb_first_diag_x1"] = relerr(ctx.download(d1, shape), c["y1"])
+        errs["cheb_first_diag_x2"] = relerr(ctx.download(d2, shape), c["y2"])
         ctx.call("spirk_op_cheb_step", C.byref(lvl), C.byref(op), dxo, dx, dxo, db, None, N, pf1, pf2)  # x_new aliases x_old
         errs["cheb_own_alias"] = relerr(ctx.download(dxo, shape), c["cheb"])
     bad = {k: v for k, v in errs.items() if not v < tol}
@@ -600,6 +685,8 @@ def run_all(dev, small=True):
     check_op_apply(dev, 3, 3, 1, OP_CASES[0])
     check_residual_and_cheb(dev, 3, 4, 1)
     check_residual_and_cheb(dev, 2, 2, 3, nb=1)
+    check_coupled_fused(dev, 3, 4, 1)
+    check_coupled_fused(dev, 2, 2, 3, ("coupled", [[2.0, 0.5], [-0.25, 3.0]], [0.1, 0.2]))
     check_apply_km(dev, 3, 4, 1)
     check_apply_km(dev, 2, 2, 3, nb=1)
     for (dim, k, r) in [(3, 4, 1), (2, 2, 3), (3, 1, 2)]:

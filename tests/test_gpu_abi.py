@@ -115,6 +115,20 @@ def test_v3_coupled_pair_full_size(gpu_dev, r, opts):
     ac.check_op_apply(gpu_dev, 3, 4, r, ("coupled", ac.so.table("A_inv", 2).tolist(), [0.1]), opts=opts)
 
 
+# k_v3<..., MODE, 4, NBC = 2> for MODE = residual / Chebyshev (explicit and own diagonal) / fused first iterations: 4 x 4-cell
+# tiles (r = 3, 4 and r = 5 under v3_small_below), 8 x 8-cell tiles (r = 5, 6), work-queue and z-lockstep schedules; unequal
+# diagonals (the general pair: the first iterations fall back to scale + step); shapes the fast path does not cover
+@pytest.mark.parametrize("dim,k,r,desc,opts", [
+    (3, 4, 2, None, {}), (3, 4, 3, None, {}), (3, 4, 4, None, {}), (3, 4, 5, None, {}), (3, 4, 5, None, {"v3_schedule": 1}),
+    (3, 4, 5, None, {"v3_small_below": 64}), (3, 4, 6, None, {}),
+    (3, 4, 4, ("coupled", [[2.0, 0.5], [-0.25, 3.0]], [0.1, 0.2]), {}), (3, 4, 5, ("coupled", [[2.0, 0.5], [-0.25, 3.0]], [0.1, 0.2]), {}),
+    (3, 4, 4, None, {"apply_variant": 1}), (2, 2, 4, None, {}), (3, 2, 2, None, {}),
+])
+def test_coupled_pair_fused_epilogues(gpu_dev, dim, k, r, desc, opts):
+    """residual / smoother kernels of the complex level operators (operator.h:616-665) against the oracle"""
+    ac.check_coupled_fused(gpu_dev, dim, k, r, desc, opts)
+
+
 @pytest.mark.parametrize("dim,k,r,nb,opts", [(3, 4, 2, 2, {}), (3, 4, 3, 1, {}), (3, 4, 4, 3, {}), (3, 4, 5, 2, {}), (3, 4, 5, 1, {"v3_schedule": 1}),
                                              (3, 4, 6, 1, {}), (2, 2, 4, 2, {}), (3, 2, 2, 4, {}), (3, 4, 1, 2, {})])
 def test_op_apply_km(gpu_dev, dim, k, r, nb, opts):
