@@ -13,26 +13,32 @@
 // Work decomposition.  A CTA owns a column of TX x TY cells (k TX x k TY node columns, "owner
 // computes": nodes [k TX tx, k TX (tx+1)) x [k TY ty, ...)) and streams it upwards in z one NODE
 // PLANE at a time through a ring of shared-memory slots:
-//   stage   : every row of the (k TX + k + 1) x (k TY + k + 1) staged nodes of `src` (owned + one
-//             cell of halo below, one node above) is ONE bulk-async copy (cp.async.bulk = TMA 1-D,
-//             completion on an mbarrier), issued two planes ahead; rows start at arbitrary 8-byte
-//             parity (n1 is odd), so a copy starts at the 16-byte aligned address below the row and
-//             the consumers add the parity.  The rows of the epilogue operands (rhs, x_old) of the
-//             same plane travel in the same slot.  No thread ever waits on a global load.
+//   stage   : the (k TX + k + 1) x (k TY + k + 1) staged nodes of `src` (owned + one cell of halo below, one node above)
+//             arrive by TMA 2-D tile copies (cp.async.bulk.tensor, completion on an mbarrier), issued NBUF - 1 planes
+//             ahead.  n1 is odd, so rows start at arbitrary 8-byte parity and no tensor map of row pitch n1 exists: the
+//             maps view PAIRS of rows as super-rows of pitch 2 n1, the staged rows of even and of odd parity are one box
+//             each, started at the 16-byte aligned element at or below the first wanted node (the consumers add the
+//             parity, a compile-time function of the plane's position in its cell layer).  The rows of the epilogue
+//             operands (rhs, x_old) of the same plane travel in the same slot.  No thread ever waits on a global load.
 //   x-phase : one thread per (staged row, cell segment): 2k+1 loads, the k owned outputs of a', c.
-//             Dirichlet / out-of-domain nodes are masked here (rows, planes and the two x-columns).
-//   y+z     : one thread per (owned x, cell segment in y), lanes along x: 2(2k+1) loads, the k owned
+//             Dirichlet / out-of-domain nodes are masked here (rows, planes and the two x-columns).  The warps without
+//             an x task combine the pointwise operands of the Chebyshev epilogue in their ring slot meanwhile.
+//   y+z     : one thread per (owned x, cell segment in y[, half of its nodes]), lanes along x: 2(2k+1) loads, the
 //             outputs of p', w, and IMMEDIATELY their contribution to the z-sums of the current
-//             cell layer, which live in registers ((k+1) planes x k nodes).  The linear part of the
+//             cell layer, which live in registers ((k+1) planes x NPT nodes).  The linear part of the
 //             fused epilogue (residual: rhs; Chebyshev: x, x_old, rhs) is folded into the z-sums
 //             when the plane passes, so when the top plane of a layer has been added, planes 0..k-1
 //             are final up to one scaling and are stored straight from registers, 256-byte
 //             coalesced per warp.  The top plane's sums carry over to the next layer.
-// No partial sums ever leave the SM: no atomics, no zero-init pass, no wall/exchange arrays, no
-// second kernel; results are bitwise reproducible.  The price is the halo: (37/32)^2 of the plane
-// is staged and 37/32 of the x-sweeps are computed for an 8 x 8-cell tile.
-// The (block, column, layer) space is split evenly over a fixed grid of 2 CTAs per SM; a piece that
-// starts above layer 0 recomputes the layer below it to obtain its incoming z-sums.
+// No partial sums are accumulated in memory: no atomics, no zero-init pass, no second kernel; results are bitwise
+// reproducible.  The price is the halo: (37/32)^2 of the plane is staged and 37/32 of the x-sweeps are computed for an
+// 8 x 8-cell tile.
+// Schedule: (block, layer range, column) work items drawn from an atomic counter by a fixed grid of 2 CTAs per SM, long
+// ranges first and short ones for the tail; the two CTAs that meet at a range boundary exchange the partial z-sums of the
+// shared vertex plane through a small buffer (nothing is recomputed; V3Args::dyn).  The even split and the z-lockstep
+// schedule of round 1 (a piece that starts above layer 0 recomputes the layer below it) remain as options.
+// Coupled pairs of blocks (NBC = 2: IRK q = 2 system matrix, complex level operators, K v + M w) stage the plane of both
+// blocks and mix the mass sweeps in the x-phase.
 //
 // Replaces the deal.II cell loop + vector updates of the reference:
 //   operator.h:298-310, 379-421 (vmult), 841-880 (batched); deal.II PreconditionChebyshev
