@@ -161,9 +161,10 @@ class Level:
         (ref operator.h:298-310, 379-421).  mass / lap may be arrays (nb,)."""
         v = u.copy()
         v[:, self.bmask] = 0.0
-        mass = np.asarray(mass, dtype=float).reshape((-1,) + (1,) * self.dim)
-        lap = np.asarray(lap, dtype=float).reshape((-1,) + (1,) * self.dim)
-        M, K = self.M1, self.K1
+        # (arithmetic in the precision of u: float64 everywhere except the FP32 V-cycle study, GMG.fp32)
+        mass = np.asarray(mass, dtype=u.dtype).reshape((-1,) + (1,) * self.dim)
+        lap = np.asarray(lap, dtype=u.dtype).reshape((-1,) + (1,) * self.dim)
+        M, K = self.M1.astype(u.dtype, copy=False), self.K1.astype(u.dtype, copy=False)
         a = self._ax(M, v, 0)
         b = self._ax(K, v, 0)
         if self.dim == 2:
@@ -444,7 +445,8 @@ class Chebyshev:
         self.theta = 0.5 * (self.max_ev + alpha)
 
     def vmult(self, b):
-        x = (1.0 / self.theta) * (self.dinv * b)
+        dinv = self.dinv.astype(b.dtype, copy=False)
+        x = (1.0 / self.theta) * (dinv * b)
         if self.degree < 2 or abs(self.delta) < 1e-40:
             return x
         xold = None
@@ -455,9 +457,9 @@ class Chebyshev:
             f1, f2 = rhokp * rhok, 2.0 * rhokp / self.delta
             rhok = rhokp
             if k == 0:
-                xn = (1.0 + f1) * x + f2 * self.dinv * (b - Ax)
+                xn = (1.0 + f1) * x + f2 * dinv * (b - Ax)
             else:
-                xn = (1.0 + f1) * x - f1 * xold + f2 * self.dinv * (b - Ax)
+                xn = (1.0 + f1) * x - f1 * xold + f2 * dinv * (b - Ax)
             xold, x = x, xn
         return x
 
@@ -484,6 +486,10 @@ class GMG:
                 Pg[2 * k * c: 2 * k * c + 2 * k + 1, k * c: k * c + k + 1] = P
             self.P1.append(Pg)
         self.smoothers = None
+        # FP32 V-cycle study (reference preconditioner.h:120-142 anticipates a float level vector): the
+        # set-up (diagonals, eigenvalue estimates, coarse inverse) stays FP64, one V-cycle runs in float32 and its result
+        # is widened again for the FP64 outer Krylov solver
+        self.fp32 = False
 
     def reinit(self, ops_for_setup=None):
         """ref preconditioner.h:341-447.  ops_for_setup lets the caller replicate SURVEY 2.4(9):
@@ -513,7 +519,7 @@ class GMG:
         lvc = self.levels[l - 1]
         v = uc.copy()
         v[:, lvc.bmask] = 0.0
-        Pg = self.P1[l - 1]
+        Pg = self.P1[l - 1].astype(uc.dtype, copy=False)
         out = v
         for ax in range(lvc.dim):
             a = out.ndim - 1 - ax
@@ -522,7 +528,7 @@ class GMG:
 
     def restrict(self, l, uf):
         lvc = self.levels[l - 1]
-        Pg = self.P1[l - 1]
+        Pg = self.P1[l - 1].astype(uf.dtype, copy=False)
         out = uf
         for ax in range(lvc.dim):
             a = out.ndim - 1 - ax
@@ -537,7 +543,7 @@ class GMG:
         lv0 = self.levels[0]
         x = b.copy()  # identity rows on constrained DoFs
         if self.coarse_inv is not None:
-            x[0][~lv0.bmask] = self.coarse_inv @ b[0][~lv0.bmask]
+            x[0][~lv0.bmask] = self.coarse_inv.astype(b.dtype, copy=False) @ b[0][~lv0.bmask]
         return x
 
     def vcycle(self, l, defect):
@@ -554,6 +560,8 @@ class GMG:
         return x
 
     def vmult(self, src):
+        if self.fp32:
+            return self.vcycle(len(self.levels) - 1, src.astype(np.float32)).astype(np.float64)
         return self.vcycle(len(self.levels) - 1, src)
 
 
@@ -854,7 +862,18 @@ def direct_irk_step(prob, q, tau, u, time):
     return unew, stages
 
 
-def run(scheme, dim, k, r, q, tau, end_time, outer_tol=1e-8, inner_tol=0.0, **kw):
+def set_fp32_vcycle(integ, on=True):
+    """switch every multigrid preconditioner of a time integrator to the float32 V-cycle (study only)"""
+    n = 0
+    for v in vars(integ).values():
+        for g in (v if isinstance(v, (list, tuple)) else [v]):
+            if isinstance(g, GMG):
+                g.fp32 = on
+                n += 1
+    return n
+
+
+def run(scheme, dim, k, r, q, tau, end_time, outer_tol=1e-8, inner_tol=0.0, fp32_vcycle=False, **kw):
     """mirror of Problem::run's time loop (ref main.cc:3298-3358).  Returns a dict of per-step
     records: errors, iteration counts, nodal l2 norm."""
     prob = Problem(dim, k, r)
@@ -867,6 +886,8 @@ def run(scheme, dim, k, r, q, tau, end_time, outer_tol=1e-8, inner_tol=0.0, **kw
         integ = ComplexIRK(prob, q, tau, outer_tol, inner_tol, batched=scheme.endswith("batched"), **kw)
     else:
         raise ValueError(scheme)
+    if fp32_vcycle:
+        assert set_fp32_vcycle(integ) > 0, "no multigrid preconditioner found"
     out = {"errors": [prob.errors(u, 0.0)], "norms": [], "prob": prob, "integ": integ}
     t = 0.0
     while end_time - t > 1e-4 * tau:
