@@ -5,11 +5,14 @@ A "step" is one fully implicit Runge-Kutta time step of the 3-D Q4 heat equation
 GMG-preconditioned GMRES on the stage system, solution update).
 
   N = 1 : BASELINE.json configs[1]: 3-D Q4, IRK q=2, GMG preconditioner, single B200.  The line also carries
-          `scaling_reference`: the N>1 workload (spirk q=8) run on this one GPU with all 8 stages batched, the N=1 point of
+          `scaling_reference`: the N>1 workload (spirk q=4) run on this one GPU with all 4 stages batched, the N=1 point of
           the strong-scaling series below.
-  N > 1 : stage-parallel SPIRK with a FIXED q = 8 stages (configs[4]'s scheme at r=6), q/N stages per GPU: a strong-scaling
-          series over N = 1, 2, 4, 8 (the outer iteration count depends on q, so only a fixed q makes the per-N values
-          comparable); fused peer-memory stage mixing + all-reduced Krylov scalars.
+  N > 1 : stage-parallel SPIRK with a FIXED q = 4 stages - the series BASELINE.json's north_star names ("a SPIRK q=4, 3D Q4
+          heat-equation time step on 8xB200 ... per-step time reported at 1/2/4/8 GPUs"): N = 2 two stages per GPU, N = 4
+          one stage per GPU (= configs[2]), N = 8 the stage x space grid of 4 stage ranks x 2 z-slabs of the mesh (the
+          north-star target configuration).  A strong-scaling series: the outer iteration count depends on q, so only a
+          fixed q makes the per-N values comparable.  Fused peer-memory stage mixing, all-reduced Krylov scalars, halo
+          exchange of the slabs.  `--stages 8` gives the q = 8 series (8 / 4 / 2 / 1 stages per GPU, profiles/).
 
 metric  : stage-DoFs advanced per second = n_dofs * q / (time per step)   [GDoF*stage/s];
           ms_per_step is the time per SPIRK step; the roofline object reports the dominant kernel
@@ -45,7 +48,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--refine", type=int, default=6, help="global refinements r: n_dofs = (4*2^r+1)^3")
     ap.add_argument("--degree", type=int, default=4)
-    ap.add_argument("--stages", type=int, default=0, help="RK stages q (default: 2 at N=1, 8 otherwise)")
+    ap.add_argument("--stages", type=int, default=0, help="RK stages q (default: 2 at N=1, 4 otherwise)")
     ap.add_argument("--no-scaling-reference", action="store_true", help="N=1: skip the spirk q=8 run on one GPU")
     ap.add_argument("--scheme", default="", help="irk | spirk | irk_batched | complex_* (default irk at N=1, spirk else)")
     ap.add_argument("--outer-tolerance", type=float, default=1e-8, help="reference default main.cc:2964")
@@ -180,7 +183,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = a.gpus
-    q = a.stages or (2 if n_gpus == 1 else 8)
+    q = a.stages or (2 if n_gpus == 1 else 4)
     if q % n_gpus and n_gpus % q:
         raise SystemExit(f"--stages {q} and --gpus {n_gpus}: one must divide the other")
     scheme = a.scheme or ("irk" if n_gpus == 1 else "spirk")
@@ -356,10 +359,10 @@ def main():
                           "algorithmic_bytes_per_dof": 16}}
     run.close()
 
-    # ---- N = 1 point of the strong-scaling series: the N > 1 workload (spirk, q = 8) with all stages batched on this GPU
+    # ---- N = 1 point of the strong-scaling series: the N > 1 workload (spirk, q = 4) with all stages batched on this GPU
     scaling_ref = None
     if n_gpus == 1 and not a.no_scaling_reference and not a.stages and not a.scheme:
-        qs, ns = 8, max(2, min(a.steps, 4))
+        qs, ns = 4, max(2, min(a.steps, 4))
         with hostapi.Run(host, params("spirk", a.degree, a.refine, qs, a.outer_tolerance, ns + 3), dim=3, device=local_rank) as r8:
             r8.setup()
             r8.set_compute_errors(False)
