@@ -42,6 +42,9 @@ def main():
           OuterTolerance=1e-8)
     write("complex_irk_batched.json", FEDegree=4, NRefinements=5, TimeIntegrationScheme="complex_irk_batched", IRKStages=4,
           EndTime=0.5, OuterTolerance=1e-8)
+    # the reference's json/spirk_sm.json (shared-memory mixing, automatic time step) at the bench size
+    write("spirk_sm.json", FEDegree=4, NRefinements=6, TimeIntegrationScheme="spirk", IRKStages=2, TimeStepSize=0.0, EndTime=0.5,
+          OuterTolerance=1e-8, Padding=0, UseSharedMemory=True)
     # config 5: large-scaling SPIRK q=8 Q4 r=7 (135 005 697 DoFs x 8 stages), scripts/default.json parameters
     write("spirk_large.json", FEDegree=4, NRefinements=7, TimeIntegrationScheme="spirk", IRKStages=8)
 
