@@ -92,3 +92,30 @@ def test_reference_ost_file_needs_the_matrix_based_path(cpu_host):
     with pytest.raises(Exception) as e:
         run_text(cpu_host, OST)
     assert "MatrixBased" in str(e.value) or "MatrixFree" in str(e.value)
+
+
+DEFAULT_JSON = """{
+    "FEDegree" : 1,
+    "NRefinements" : 3,
+    "TimeIntegrationScheme" : "spirk",
+    "IRKStages" : "4",
+    "OuterTolerance" : "1e-12",
+    "InnerTolerance" : "0.0",
+    "TimeStepSize" : "0.1",
+    "EndTime" : "1.0",
+    "OperatorType" : "MatrixFree",
+    "BlockPreconditionerType" : "GMG",
+    "DoRowMajor" : true,
+    "Padding" : -1,
+    "DoOutputParaview" : false,
+    "MaxRanks" : 4
+}"""
+
+
+def test_reference_scaling_template(cpu_host):
+    """scripts/default.json, the template of the reference's scaling studies (every key its generator scripts set)"""
+    res = run_text(cpu_host, DEFAULT_JSON)
+    ora = so.run("spirk", 2, 1, 3, 4, 0.1, 1.0, outer_tol=1e-12)
+    assert len(res["outer"]) == 10
+    assert np.all(np.abs(res["outer"] - np.array(ora["integ"].n_outer)) <= 1)
+    assert np.allclose(res["error_L2"], np.array(ora["errors"])[:, 0], rtol=1e-7)
