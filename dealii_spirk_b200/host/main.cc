@@ -2,10 +2,11 @@
 // parameter file, run back to back, one statistics table at the end.  The dimension (the
 // reference's compile-time IRK_DIMENSION, CMakeLists.txt:38-46) is the optional first argument
 // "--dim=2|3" (default 3).  Single process / single GPU; multi-GPU runs are launched through
-// `python -m dealii_spirk_b200.run` (one process per GPU, NCCL id exchanged by torch.distributed).
+// `python -m dealii_spirk_b200.launch` (one process per GPU, NCCL id exchanged by torch.distributed).
 #include <spirk_host.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 
